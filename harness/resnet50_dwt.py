@@ -1,0 +1,169 @@
+"""ResNet-50-DWT measurement harness (the model the hot-path layers drop into).
+
+The reference model lives in its experiment script
+(/root/reference/resnet50_dwt_mec_officehome.py:40-378), which cannot travel to
+the GPU box and is out of scope to rebuild.  This file re-states
+only its *topology* so that ``bench.py`` and the parity tests have something to
+drop the layers into: a torchvision-style ResNet-50 whose every norm site is a
+domain triple (source | target | target-aug), whitening in the stem and layer1,
+domain batch-norm in layers 2-4, one shared gamma/beta per site.
+
+Parameter and buffer names match the reference model one-for-one, so a state
+dict produced for one loads into the other (``tests/test_harness_vs_reference``
+checks logits/loss/grads against the unmodified reference script in the build
+container).  The norm layers come from a ``layers`` namespace -- the product
+package ``dwt_b200`` by default, the CPU oracle port in CPU tests:
+
+    layers.WTransform2d, layers.BatchNorm2d           (reference-compatible ctors)
+    layers.DomainTripleNorm (optional)                (fused site)
+
+``site_mode``:
+    "modules"  reference composition: split/3 -> 3 modules -> cat -> *gamma+beta -> relu
+               (resnet50_dwt_mec_officehome.py:220-222,335-337)
+    "fused"    one DomainTripleNorm call per site (needs layers.DomainTripleNorm)
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+_STAGES = ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2))   # planes, blocks, stride
+_DOMAINS = ("s", "t", "t_aug")                                   # bns*, bnt*, bnt*_aug
+EXPANSION = 4
+
+
+class WhitenScaleShift(nn.Module):
+    """Same role and attribute names as the reference's ``whitening_scale_shift``
+    (resnet50_dwt_mec_officehome.py:40-63): ``.wh`` is the whitening transform,
+    optional per-channel ``gamma``/``beta``."""
+
+    def __init__(self, layers, planes, group_size, running_mean, running_variance,
+                 track_running_stats=True, affine=True):
+        super().__init__()
+        self.planes, self.group_size, self.affine = planes, group_size, affine
+        self.wh = layers.WTransform2d(planes, group_size, running_m=running_mean,
+                                      running_var=running_variance,
+                                      track_running_stats=track_running_stats)
+        if affine:
+            self.gamma = nn.Parameter(torch.ones(planes, 1, 1))
+            self.beta = nn.Parameter(torch.zeros(planes, 1, 1))
+
+    def forward(self, x):
+        y = self.wh(x)
+        return y * self.gamma + self.beta if self.affine else y
+
+
+class _SiteOwner(nn.Module):
+    """Mixin: registers a domain-triple norm site under the reference's flat names
+    (``bns1/bnt1/bnt1_aug/gamma1/beta1`` ...) and runs it."""
+
+    def _add_site(self, layers, tag, key, planes, whiten, group_size, stats, site_mode):
+        # tag: "1"/"2"/"3" -> bns{tag}, gamma{tag};  "downsample" -> downsample_bns, downsample_gamma
+        pre, post = ("downsample_", "") if tag == "downsample" else ("", tag)
+        names = [f"{pre}bn{d}{post}" if d != "t_aug" else f"{pre}bnt{post}_aug" for d in _DOMAINS]
+        if whiten:
+            rm, rv = stats[key + ".wh.running_mean"], stats[key + ".wh.running_variance"]
+            gamma, beta = stats[key + ".gamma"], stats[key + ".beta"]
+            mods = [WhitenScaleShift(layers, planes, group_size, rm, rv, affine=False) for _ in names]
+        else:
+            rm, rv = stats[key + ".running_mean"], stats[key + ".running_var"]
+            gamma, beta = stats[key + ".weight"].view(-1, 1, 1), stats[key + ".bias"].view(-1, 1, 1)
+            mods = [layers.BatchNorm2d(num_features=planes, running_m=rm, running_v=rv, affine=False)
+                    for _ in names]
+        for n, m in zip(names, mods):
+            setattr(self, n, m)
+        gname = f"{pre}gamma{post}" if pre == "" else "downsample_gamma"
+        bname = f"{pre}beta{post}" if pre == "" else "downsample_beta"
+        setattr(self, gname, nn.Parameter(gamma))
+        setattr(self, bname, nn.Parameter(beta))
+        if not hasattr(self, "_sites"):
+            self._sites = {}
+        self._sites[tag] = (names, gname, bname, whiten)
+        if site_mode == "fused":
+            # not registered as a submodule: it owns no state, only borrows the
+            # three modules' buffers and the site's gamma/beta at call time.
+            object.__setattr__(self, f"_fused_{tag}", layers.DomainTripleNorm(
+                kind="whiten" if whiten else "bn", num_features=planes,
+                group_size=group_size if whiten else 1))
+
+    def _site(self, tag, x, relu):
+        names, gname, bname, whiten = self._sites[tag]
+        gamma, beta = getattr(self, gname), getattr(self, bname)
+        if self.training:
+            fused = getattr(self, f"_fused_{tag}", None)
+            mods = [getattr(self, n) for n in names]
+            if fused is not None:
+                return fused(x, [m.wh if whiten else m for m in mods], gamma, beta, relu)
+            parts = torch.split(x, x.shape[0] // 3, dim=0)
+            s, t, a = (m(p) for m, p in zip(mods, parts))
+            out = torch.cat((s, torch.cat((t, a), dim=0)), dim=0) * gamma + beta
+        else:
+            out = getattr(self, names[1])(x) * gamma + beta      # target branch only (:241-260)
+        return torch.relu_(out) if relu else out
+
+
+class Bottleneck(_SiteOwner):
+    def __init__(self, layers, inplanes, planes, layer, sub_layer, stats, group_size, stride,
+                 downsample, site_mode):
+        super().__init__()
+        whiten = layer == 1
+        key = f"layer{layer}.{sub_layer}"
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self._add_site(layers, "1", key + ".bn1", planes, whiten, group_size, stats, site_mode)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self._add_site(layers, "2", key + ".bn2", planes, whiten, group_size, stats, site_mode)
+        self.conv3 = nn.Conv2d(planes, planes * EXPANSION, 1, bias=False)
+        self._add_site(layers, "3", key + ".bn3", planes * EXPANSION, whiten, group_size, stats, site_mode)
+        self.downsample = downsample
+        if downsample is not None:
+            self._add_site(layers, "downsample", f"layer{layer}.0.downsample_bn", planes * EXPANSION,
+                           whiten, group_size, stats, site_mode)
+
+    def forward(self, x):
+        out = self._site("1", self.conv1(x), relu=True)
+        out = self._site("2", self.conv2(out), relu=True)
+        out = self._site("3", self.conv3(out), relu=False)
+        identity = x if self.downsample is None else self._site("downsample", self.downsample(x), relu=False)
+        return torch.relu_(out + identity)
+
+
+class ResNet50DWT(_SiteOwner):
+    def __init__(self, layers, state_dict, num_classes=65, group_size=4, site_mode="modules"):
+        super().__init__()
+        if site_mode not in ("modules", "fused"):
+            raise ValueError("site_mode must be 'modules' or 'fused'")
+        stats = {k: v for k, v in state_dict.items() if "bn" in k or "downsample" in k}
+        self.site_mode = site_mode
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self._add_site(layers, "1", "bn1", 64, True, group_size, stats, site_mode)
+        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        inplanes = 64
+        for li, (planes, blocks, stride) in enumerate(_STAGES, start=1):
+            seq = []
+            for b in range(blocks):
+                down = None
+                if b == 0 and (stride != 1 or inplanes != planes * EXPANSION):
+                    down = nn.Sequential(nn.Conv2d(inplanes, planes * EXPANSION, 1, stride=stride, bias=False))
+                # the reference's _make_layer never forwards ResNet's group_size (:316,325,328): always 4
+                seq.append(Bottleneck(layers, inplanes, planes, li, b, stats, 4, stride if b == 0 else 1,
+                                      down, site_mode))
+                inplanes = planes * EXPANSION
+            setattr(self, f"layer{li}", nn.Sequential(*seq))
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc_out = nn.Linear(512 * EXPANSION, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    def forward(self, x):
+        x = self.maxpool(self._site("1", self.conv1(x), relu=True))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return self.fc_out(torch.flatten(self.avgpool(x), 1))
+
+
+def build_resnet50_dwt(state_dict, layers, site_mode="modules", num_classes=65):
+    """state_dict uses the reference checkpoint's key names *without* the 7-char
+    ``module.`` prefix (resnet50_dwt_mec_officehome.py:370-376)."""
+    model = ResNet50DWT(layers, state_dict, num_classes=num_classes, site_mode=site_mode)
+    model.load_state_dict(state_dict, strict=False)
+    return model
