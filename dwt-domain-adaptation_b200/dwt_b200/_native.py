@@ -1,0 +1,138 @@
+"""ctypes binding of libdwt_b200.so (include/dwt_b200.h) -- the only way the Python layers
+reach the GPU.  There is no CPU path: if the library is missing or the tensors are not on a
+CUDA device the call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdwt_b200.so")
+
+ABI_VERSION = 1
+MAX_DOMAINS = 4
+MAX_GROUP_SIZE = 64
+MODE_TRAIN, MODE_EVAL = 0, 1
+EPI_NONE, EPI_AFFINE, EPI_RELU = 0, 1, 2
+
+_c_float_p = ctypes.c_void_p
+_PtrArray = ctypes.c_void_p * MAX_DOMAINS
+
+_SIGNATURES = {
+    "dwt_abi_version": (ctypes.c_int, []),
+    "dwt_last_error": (ctypes.c_char_p, []),
+    "dwt_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
+    "dwt_whiten_fwd": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                      ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                      _c_float_p, _c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p,
+                                      ctypes.c_size_t, ctypes.c_void_p]),
+    "dwt_whiten_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64,
+                                      ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                      _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, _c_float_p,
+                                      _c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "dwt_bn_fwd": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                  ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), _c_float_p,
+                                  _c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t,
+                                  ctypes.c_void_p]),
+    "dwt_bn_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                  ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                  ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t,
+                                  ctypes.c_void_p]),
+    "dwt_mec_fwd_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, _c_float_p,
+                                       _c_float_p, _c_float_p, ctypes.c_void_p]),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the shared library; raise if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise NativeError(
+                        f"{LIB_PATH} is missing: build it with `python {os.path.join(_HERE, 'build.py')}` "
+                        "(dwt_b200 has no CPU or PyTorch fallback)")
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype, fn.argtypes = res, args
+                if handle.dwt_abi_version() != ABI_VERSION:
+                    raise NativeError("libdwt_b200.so ABI version mismatch; rebuild it")
+                _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise NativeError(f"libdwt_b200 error {rc}: {lib().dwt_last_error().decode()}")
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def ptr_array(tensors):
+    arr = _PtrArray()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))
+
+
+def require_cuda(*tensors) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise NativeError("dwt_b200 runs on CUDA tensors only (no CPU fallback); got a tensor on " + str(t.device))
+        if t.dtype != torch.float32:
+            raise NativeError("dwt_b200 computes in float32; got " + str(t.dtype))
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise NativeError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# One zero-initialised, grow-only workspace per (device, stream): kernels of one stream run in
+# order, so they can share it; the arrival counters inside reset themselves.
+_workspaces: dict = {}
+
+
+def workspace(device, n, c, hw, gs, nd):
+    need = lib().dwt_workspace_bytes(n, c, hw, gs, nd)
+    if need == 0:
+        raise NativeError(f"invalid geometry for workspace: C={c} group_size={gs} domains={nd}")
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def status(device=None) -> int:
+    """Device status word of the current stream's workspace (syncs).  Bit 0: a covariance was
+    not positive definite (the reference raises from torch.cholesky at that point)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    buf = _workspaces.get((device.index, torch.cuda.current_stream(device).cuda_stream))
+    return 0 if buf is None else int(buf[:4].view(torch.int32).item())

@@ -1,0 +1,270 @@
+// C ABI of libdwt_b200.so (declared in include/dwt_b200.h): argument validation, workspace
+// carving, kernel-family selection by group size, launches.  No host synchronisation, no
+// allocation, no CPU fallback.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <mutex>
+
+#include "norm_launch.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(DWT_E_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
+  }
+  return DWT_OK;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;   // B200
+  }
+  return n;
+}
+
+std::once_flag g_tiled_once;
+int g_tiled_rc = 0;
+int ensure_tiled() {
+  std::call_once(g_tiled_once, [] { g_tiled_rc = dwt::tiled_init(); });
+  return g_tiled_rc;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Upper bound of CTAs cooperating on one (domain, group): enough CTAs to fill the machine
+// a few times over, split evenly over the D*G independent problems.
+int chunk_cap(int GS, int G, int D) {
+  const int target = sm_count() * (GS <= 4 ? 8 : 2);
+  int cap = (target + G * D - 1) / (G * D);
+  return cap < 1 ? 1 : cap;
+}
+
+struct Workspace {
+  int* status;
+  int* counters;      // [D*G]
+  int* dom_counter;   // [G]   (forward)
+  int* dom_counter2;  // [G]   (backward)
+  float* partial;     // [D*G*cap*(GS*GS+GS)]
+  float* save_cov;    // [D*G*GS*GS]
+  float* coef;        // [D*G*(2*GS*GS+GS)]
+  float* dgb_part;    // [D*2*C]
+  size_t bytes;
+};
+
+Workspace carve(void* base, int64_t C, int GS, int D) {
+  const int G = (int)(C / GS);
+  const int cap = chunk_cap(GS, G, D);
+  size_t off = 0;
+  auto take = [&](size_t nbytes) { size_t o = off; off = align_up(off + nbytes, 256); return o; };
+  char* b = static_cast<char*>(base);
+  Workspace w;
+  w.status = reinterpret_cast<int*>(b + take(sizeof(int)));
+  w.counters = reinterpret_cast<int*>(b + take(sizeof(int) * (size_t)D * G));
+  w.dom_counter = reinterpret_cast<int*>(b + take(sizeof(int) * (size_t)G));
+  w.dom_counter2 = reinterpret_cast<int*>(b + take(sizeof(int) * (size_t)G));
+  w.partial = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * cap * (GS * GS + GS)));
+  w.save_cov = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * GS * GS));
+  w.coef = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * dwt::coef_stride(GS)));
+  w.dgb_part = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * 2 * C));
+  w.bytes = off;
+  return w;
+}
+
+struct Plan {
+  dwt::Geom gm;
+  int vec;        // 4 when rows can be read as float4
+  int chunks_ew;  // grid.x of the elementwise (apply) kernels
+  bool small;
+};
+
+int make_plan(Plan& p, const void* a0, const void* a1, const void* a2, int64_t N, int64_t C, int64_t HW, int GS,
+              int D) {
+  if (N <= 0 || C <= 0 || HW <= 0) return fail(DWT_E_INVALID, "empty tensor (N=%lld C=%lld HW=%lld)", (long long)N,
+                                               (long long)C, (long long)HW);
+  if (GS < 1 || GS > DWT_MAX_GROUP_SIZE) return fail(DWT_E_UNSUPPORTED, "group_size %d outside [1,%d]", GS,
+                                                     DWT_MAX_GROUP_SIZE);
+  if (C % GS != 0) return fail(DWT_E_INVALID, "channels %lld not divisible by group_size %d", (long long)C, GS);
+  if (D < 1 || D > DWT_MAX_DOMAINS) return fail(DWT_E_INVALID, "n_domains %d outside [1,%d]", D, DWT_MAX_DOMAINS);
+  if (N * HW >= (int64_t)1 << 31 || C * HW >= (int64_t)1 << 31 || C / GS > 65535)
+    return fail(DWT_E_UNSUPPORTED, "shape too large for 32-bit item indexing");
+  dwt::Geom& g = p.gm;
+  g.N = (int)N; g.C = (int)C; g.HW = (int)HW; g.GS = GS; g.G = (int)(C / GS); g.D = D;
+  g.M = (float)((double)N * (double)HW);
+  const uintptr_t bits = (uintptr_t)a0 | (uintptr_t)a1 | (uintptr_t)a2;
+  p.vec = (HW % 4 == 0 && bits % 16 == 0) ? 4 : 1;
+  p.small = dwt::small_supports(GS);
+  const int cap = chunk_cap(GS, g.G, D);
+  int64_t work_units;   // CTA-iterations available per (domain, group)
+  if (p.small) work_units = (N * (HW / p.vec) + dwt::kThreads * 4 - 1) / (dwt::kThreads * 4);
+  else work_units = (N * HW + 127) / 128;
+  if (work_units < 1) work_units = 1;
+  g.nchunks = (int)(work_units < cap ? work_units : cap);
+  const int ew_cap = cap * 2;
+  p.chunks_ew = (int)(work_units < ew_cap ? work_units : ew_cap);
+  return DWT_OK;
+}
+
+int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, int GS, int D, int mode, float a,
+                    float b, float momentum, float unbias, int update_running, float* const* rmean,
+                    float* const* rcov, const float* gamma, const float* beta, int epi, float* save_mean,
+                    float* save_w, void* ws, size_t ws_bytes, cudaStream_t st) {
+  Plan p;
+  if (int rc = make_plan(p, x, y, nullptr, N, C, HW, GS, D)) return rc;
+  if (!x || !y || !save_mean || !save_w || !ws) return fail(DWT_E_INVALID, "null pointer argument");
+  if (mode != DWT_MODE_TRAIN && mode != DWT_MODE_EVAL) return fail(DWT_E_INVALID, "bad mode %d", mode);
+  if ((epi & DWT_EPI_RELU) && !(epi & DWT_EPI_AFFINE)) return fail(DWT_E_INVALID, "RELU epilogue needs AFFINE");
+  if ((epi & DWT_EPI_AFFINE) && (!gamma || !beta)) return fail(DWT_E_INVALID, "AFFINE epilogue needs gamma and beta");
+  if (epi != 0 && !p.small)
+    return fail(DWT_E_UNSUPPORTED, "fused gamma/beta/ReLU epilogue is built for group_size 1, 2, 4 (got %d)", GS);
+  const bool need_running = (mode == DWT_MODE_EVAL) || update_running;
+  if (need_running) {
+    if (!rmean || !rcov) return fail(DWT_E_INVALID, "running buffers required");
+    for (int d = 0; d < D; ++d)
+      if (!rmean[d] || !rcov[d]) return fail(DWT_E_INVALID, "running buffer of domain %d is null", d);
+  }
+  Workspace w = carve(ws, C, GS, D);
+  if (w.bytes > ws_bytes) return fail(DWT_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes);
+  if ((uintptr_t)ws % 256 != 0) return fail(DWT_E_WORKSPACE, "workspace must be 256-byte aligned");
+  if (!p.small && ensure_tiled() != 0) return fail(DWT_E_LAUNCH, "cudaFuncSetAttribute failed (%d)", g_tiled_rc);
+
+  dwt::FwdFin fin{};
+  fin.a = a; fin.b = b; fin.momentum = momentum; fin.unbias = unbias;
+  fin.update_running = (mode == DWT_MODE_TRAIN) ? update_running : 0;
+  fin.save_mean = save_mean; fin.save_w = save_w; fin.save_cov = w.save_cov;
+  for (int d = 0; d < D; ++d) { fin.rmean[d] = need_running ? rmean[d] : nullptr; fin.rcov[d] = need_running ? rcov[d] : nullptr; }
+  fin.dom_counter = w.dom_counter; fin.status = w.status;
+
+  if (mode == DWT_MODE_TRAIN) {
+    if (p.small) dwt::small_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
+    else dwt::tiled_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
+  } else {
+    if (p.small) dwt::small_eval_prep(p.gm, fin, st);
+    else dwt::tiled_eval_prep(p.gm, fin, st);
+  }
+  if (int rc = check_launch("whitening statistics kernel")) return rc;
+  if (p.small) dwt::small_apply(x, y, p.gm, p.vec, p.chunks_ew, epi, save_mean, save_w, gamma, beta, st);
+  else dwt::tiled_apply(x, y, p.gm, p.vec, p.chunks_ew, save_mean, save_w, st);
+  return check_launch("whitening apply kernel");
+}
+
+int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int64_t C, int64_t HW, int GS, int D,
+                    int mode, float a, const float* save_mean, const float* save_w, const float* gamma,
+                    const float* beta, int epi, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
+  Plan p;
+  if (int rc = make_plan(p, x, dout, dx, N, C, HW, GS, D)) return rc;
+  if (!x || !dout || !dx || !save_mean || !save_w || !ws) return fail(DWT_E_INVALID, "null pointer argument");
+  if (mode != DWT_MODE_TRAIN && mode != DWT_MODE_EVAL) return fail(DWT_E_INVALID, "bad mode %d", mode);
+  if ((epi & DWT_EPI_RELU) && !(epi & DWT_EPI_AFFINE)) return fail(DWT_E_INVALID, "RELU epilogue needs AFFINE");
+  if ((epi & DWT_EPI_AFFINE) && (!gamma || !beta)) return fail(DWT_E_INVALID, "AFFINE epilogue needs gamma and beta");
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return fail(DWT_E_INVALID, "dgamma and dbeta go together");
+  if (epi != 0 && !p.small)
+    return fail(DWT_E_UNSUPPORTED, "fused gamma/beta/ReLU epilogue is built for group_size 1, 2, 4 (got %d)", GS);
+  Workspace w = carve(ws, C, GS, D);
+  if (w.bytes > ws_bytes) return fail(DWT_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, ws_bytes);
+  if ((uintptr_t)ws % 256 != 0) return fail(DWT_E_WORKSPACE, "workspace must be 256-byte aligned");
+  if (!p.small && ensure_tiled() != 0) return fail(DWT_E_LAUNCH, "cudaFuncSetAttribute failed (%d)", g_tiled_rc);
+
+  dwt::BwdFin fin{};
+  fin.a = a; fin.mode = mode; fin.epi = epi;
+  fin.save_mean = save_mean; fin.save_w = save_w; fin.gamma = gamma;
+  fin.coef = w.coef; fin.dgb_part = w.dgb_part;
+  fin.dgamma = (epi & DWT_EPI_AFFINE) ? dgamma : nullptr;
+  fin.dbeta = (epi & DWT_EPI_AFFINE) ? dbeta : nullptr;
+  fin.dom_counter = w.dom_counter2;
+
+  const bool need_reduce = (mode == DWT_MODE_TRAIN) || (fin.dgamma != nullptr);
+  if (need_reduce) {
+    if (p.small) dwt::small_bwd_reduce(x, dout, p.gm, p.vec, fin, beta, w.partial, w.counters, st);
+    else dwt::tiled_bwd_reduce(x, dout, p.gm, p.vec, fin, w.partial, w.counters, st);
+  } else {
+    if (p.small) dwt::small_bwd_prep(p.gm, fin, st);
+    else dwt::tiled_bwd_prep(p.gm, fin, st);
+  }
+  if (int rc = check_launch("whitening backward reduction kernel")) return rc;
+  if (p.small) dwt::small_bwd_apply(x, dout, dx, p.gm, p.vec, p.chunks_ew, epi, w.coef, save_mean, save_w, gamma, beta, st);
+  else dwt::tiled_bwd_apply(x, dout, dx, p.gm, p.vec, p.chunks_ew, w.coef, st);
+  return check_launch("whitening backward apply kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+int dwt_abi_version(void) { return DWT_B200_ABI_VERSION; }
+
+const char* dwt_last_error(void) { return g_err; }
+
+size_t dwt_workspace_bytes(int64_t N, int64_t C, int64_t HW, int group_size, int n_domains) {
+  (void)N; (void)HW;
+  if (C <= 0 || group_size < 1 || group_size > DWT_MAX_GROUP_SIZE || C % group_size != 0 || n_domains < 1 ||
+      n_domains > DWT_MAX_DOMAINS)
+    return 0;
+  return carve(nullptr, C, group_size, n_domains).bytes;
+}
+
+int dwt_whiten_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, int group_size, int n_domains,
+                   int mode, float eps, float momentum, int update_running, float* const* running_mean,
+                   float* const* running_cov, const float* gamma, const float* beta, int epilogue, float* save_mean,
+                   float* save_w, void* workspace, size_t workspace_bytes, dwt_stream_t stream) {
+  return whiten_like_fwd(x, y, N, C, HW, group_size, n_domains, mode, 1.f - eps, eps, momentum, 1.f, update_running,
+                         running_mean, running_cov, gamma, beta, epilogue, save_mean, save_w, workspace,
+                         workspace_bytes, (cudaStream_t)stream);
+}
+
+int dwt_whiten_bwd(const float* x, const float* dout, float* dx, int64_t N, int64_t C, int64_t HW, int group_size,
+                   int n_domains, int mode, float eps, const float* save_mean, const float* save_w,
+                   const float* gamma, const float* beta, int epilogue, float* dgamma, float* dbeta, void* workspace,
+                   size_t workspace_bytes, dwt_stream_t stream) {
+  return whiten_like_bwd(x, dout, dx, N, C, HW, group_size, n_domains, mode, 1.f - eps, save_mean, save_w, gamma,
+                         beta, epilogue, dgamma, dbeta, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// Batch norm is the group-size-1 member of the same family: "covariance" = biased variance,
+// S = var + eps, W = 1/sqrt(S) = invstd; only the EMA differs (unbiased variance).
+int dwt_bn_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, int n_domains, int mode, float eps,
+               float factor, int update_running, float* const* running_mean, float* const* running_var,
+               const float* weight, const float* bias, int epilogue, float* save_mean, float* save_invstd,
+               void* workspace, size_t workspace_bytes, dwt_stream_t stream) {
+  const double M = (double)N * (double)HW;
+  const float unbias = M > 1.0 ? (float)(M / (M - 1.0)) : 1.f;
+  return whiten_like_fwd(x, y, N, C, HW, 1, n_domains, mode, 1.f, eps, factor, unbias, update_running, running_mean,
+                         running_var, weight, bias, epilogue, save_mean, save_invstd, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
+}
+
+int dwt_bn_bwd(const float* x, const float* dout, float* dx, int64_t N, int64_t C, int64_t HW, int n_domains,
+               int mode, const float* save_mean, const float* save_invstd, const float* weight, const float* bias,
+               int epilogue, float* dweight, float* dbias, void* workspace, size_t workspace_bytes,
+               dwt_stream_t stream) {
+  return whiten_like_bwd(x, dout, dx, N, C, HW, 1, n_domains, mode, 1.f, save_mean, save_invstd, weight, bias,
+                         epilogue, dweight, dbias, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dwt_mec_fwd_bwd(const float* x, const float* y, int64_t N, int64_t K, float* loss, float* gx, float* gy,
+                    dwt_stream_t stream) {
+  if (!x || !y || !loss || !gx || !gy) return fail(DWT_E_INVALID, "null pointer argument");
+  if (N <= 0 || K <= 0 || N >= (1 << 24) || K >= (1 << 24)) return fail(DWT_E_INVALID, "bad logits shape [%lld,%lld]", (long long)N, (long long)K);
+  dwt::mec_launch(x, y, (int)N, (int)K, loss, gx, gy, (cudaStream_t)stream);
+  return check_launch("MEC kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,38 @@
+// Host-side launch entry points of the kernel families (internal to libdwt_b200.so).
+#pragma once
+#include "dwt_common.cuh"
+
+namespace dwt {
+
+// register-resident path, GS in {1,2,4}  (norm_small.cu)
+bool small_supports(int GS);
+void small_stats(const float* x, const Geom& gm, int vec, const FwdFin& fin, float* partial, int* counters,
+                 cudaStream_t st);
+void small_eval_prep(const Geom& gm, const FwdFin& fin, cudaStream_t st);
+void small_apply(const float* x, float* y, const Geom& gm, int vec, int chunks, int epi, const float* mean,
+                 const float* w, const float* gamma, const float* beta, cudaStream_t st);
+void small_bwd_reduce(const float* x, const float* dout, const Geom& gm, int vec, const BwdFin& fin,
+                      const float* beta, float* partial, int* counters, cudaStream_t st);
+void small_bwd_prep(const Geom& gm, const BwdFin& fin, cudaStream_t st);
+void small_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int vec, int chunks, int epi,
+                     const float* coef, const float* mean, const float* w, const float* gamma, const float* beta,
+                     cudaStream_t st);
+
+// shared-memory tiled path, any GS <= 64  (norm_tiled.cu)
+int tiled_smem_bytes(int GS);
+int tiled_init();   // opt in to large dynamic shared memory; returns cudaError_t as int
+void tiled_stats(const float* x, const Geom& gm, int vec, const FwdFin& fin, float* partial, int* counters,
+                 cudaStream_t st);
+void tiled_eval_prep(const Geom& gm, const FwdFin& fin, cudaStream_t st);
+void tiled_apply(const float* x, float* y, const Geom& gm, int vec, int chunks, const float* mean, const float* w,
+                 cudaStream_t st);
+void tiled_bwd_reduce(const float* x, const float* dout, const Geom& gm, int vec, const BwdFin& fin, float* partial,
+                      int* counters, cudaStream_t st);
+void tiled_bwd_prep(const Geom& gm, const BwdFin& fin, cudaStream_t st);
+void tiled_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int vec, int chunks,
+                     const float* coef, cudaStream_t st);
+
+// MEC loss (mec.cu)
+void mec_launch(const float* x, const float* y, int N, int K, float* loss, float* gx, float* gy, cudaStream_t st);
+
+}  // namespace dwt

@@ -1,0 +1,127 @@
+"""autograd Functions over the C ABI: one forward call + one hand-derived backward call each.
+
+Saved for backward: the layer input x plus the tiny per-group statistics (mean, W) -- never a
+centred copy, a transposed copy or the covariance graph the reference's autograd keeps
+(utils/whitening.py:44-55).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as nv
+
+
+def _as_nchw(x: torch.Tensor):
+    """[N, C, *spatial] -> contiguous tensor, (N, C, HW)."""
+    if not x.is_contiguous():
+        x = x.contiguous()
+    n, c = x.shape[0], x.shape[1]
+    hw = 1
+    for s in x.shape[2:]:
+        hw *= s
+    return x, n, c, hw
+
+
+class _NormFunction(torch.autograd.Function):
+    """Shared by whitening (kind='whiten') and domain batch norm (kind='bn').
+
+    x is [n_domains*N, C, *]; `running` is a list of n_domains (mean, second-moment) buffer pairs
+    (entries may alias); gamma/beta are [C]-sized or None; relu fuses max(.,0) behind the affine.
+    """
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, kind, group_size, n_domains, mode, eps, momentum, update_running,
+                running, relu):
+        lib = nv.lib()
+        x, n_all, c, hw = _as_nchw(x)
+        if n_all % n_domains != 0:
+            raise ValueError(f"batch of {n_all} does not split into {n_domains} domains")
+        n = n_all // n_domains
+        dev = nv.require_cuda(x, gamma, beta, *[t for pair in running for t in pair])
+        epi = nv.EPI_NONE
+        if gamma is not None:
+            epi = nv.EPI_AFFINE | (nv.EPI_RELU if relu else 0)
+            gamma_c, beta_c = gamma.detach().reshape(-1).contiguous(), beta.detach().reshape(-1).contiguous()
+        else:
+            gamma_c = beta_c = None
+        gs = group_size if kind == "whiten" else 1
+        y = torch.empty_like(x)
+        save_mean = torch.empty(n_domains, c, dtype=torch.float32, device=dev)
+        save_w = torch.empty(n_domains, c // gs, gs, gs, dtype=torch.float32, device=dev)
+        ws = nv.workspace(dev, n, c, hw, gs, n_domains)
+        need_running = (mode == nv.MODE_EVAL) or update_running
+        rm = nv.ptr_array([p[0] for p in running]) if need_running else None
+        rv = nv.ptr_array([p[1] for p in running]) if need_running else None
+        with torch.cuda.device(dev):
+            if kind == "whiten":
+                rc = lib.dwt_whiten_fwd(nv.ptr(x), nv.ptr(y), n, c, hw, gs, n_domains, mode, eps, momentum,
+                                        int(update_running), rm, rv, nv.ptr(gamma_c), nv.ptr(beta_c), epi,
+                                        nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
+            else:
+                rc = lib.dwt_bn_fwd(nv.ptr(x), nv.ptr(y), n, c, hw, n_domains, mode, eps, momentum,
+                                    int(update_running), rm, rv, nv.ptr(gamma_c), nv.ptr(beta_c), epi,
+                                    nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
+        nv.check(rc)
+        ctx.save_for_backward(x, save_mean, save_w, gamma_c, beta_c)
+        ctx.cfg = (kind, gs, n_domains, mode, eps, epi, n, c, hw, None if gamma is None else gamma.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = nv.lib()
+        x, save_mean, save_w, gamma_c, beta_c = ctx.saved_tensors
+        kind, gs, n_domains, mode, eps, epi, n, c, hw, gshape = ctx.cfg
+        dout = dout.contiguous()
+        dev = nv.require_cuda(dout)
+        dx = torch.empty_like(x)
+        want_affine = gamma_c is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        dgamma = torch.empty(c, dtype=torch.float32, device=dev) if want_affine else None
+        dbeta = torch.empty(c, dtype=torch.float32, device=dev) if want_affine else None
+        ws = nv.workspace(dev, n, c, hw, gs, n_domains)
+        with torch.cuda.device(dev):
+            if kind == "whiten":
+                rc = lib.dwt_whiten_bwd(nv.ptr(x), nv.ptr(dout), nv.ptr(dx), n, c, hw, gs, n_domains, mode, eps,
+                                        nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(gamma_c), nv.ptr(beta_c), epi,
+                                        nv.ptr(dgamma), nv.ptr(dbeta), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
+            else:
+                rc = lib.dwt_bn_bwd(nv.ptr(x), nv.ptr(dout), nv.ptr(dx), n, c, hw, n_domains, mode,
+                                    nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(gamma_c), nv.ptr(beta_c), epi,
+                                    nv.ptr(dgamma), nv.ptr(dbeta), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
+        nv.check(rc)
+        if want_affine:
+            dgamma, dbeta = dgamma.view(gshape), dbeta.view(gshape)
+        return (dx, dgamma, dbeta) + (None,) * 9
+
+
+def norm(x, gamma, beta, *, kind, group_size, n_domains, training_stats, eps, momentum, update_running,
+         running, relu=False):
+    mode = nv.MODE_TRAIN if training_stats else nv.MODE_EVAL
+    return _NormFunction.apply(x, gamma, beta, kind, group_size, n_domains, mode, float(eps), float(momentum),
+                               bool(update_running), running, bool(relu))
+
+
+class _MecFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        lib = nv.lib()
+        if x.dim() != 2 or x.shape != y.shape:
+            raise ValueError(f"expected two [N, K] logit tensors, got {tuple(x.shape)} and {tuple(y.shape)}")
+        x, y = x.contiguous(), y.contiguous()
+        dev = nv.require_cuda(x, y)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        gx, gy = torch.empty_like(x), torch.empty_like(y)
+        with torch.cuda.device(dev):
+            rc = lib.dwt_mec_fwd_bwd(nv.ptr(x), nv.ptr(y), x.shape[0], x.shape[1], nv.ptr(loss), nv.ptr(gx),
+                                     nv.ptr(gy), nv.stream_ptr(dev))
+        nv.check(rc)
+        ctx.save_for_backward(gx, gy)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        gx, gy = ctx.saved_tensors
+        return g * gx, g * gy
+
+
+def mec_loss(x, y):
+    return _MecFunction.apply(x, y)

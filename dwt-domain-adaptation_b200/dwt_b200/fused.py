@@ -1,0 +1,55 @@
+"""Fused domain-triple norm site (extension beyond the reference's module API).
+
+The reference runs every norm site as
+    split/3 -> bns(x_s) | bnt(x_t) | bnt_aug(x_t') -> cat -> cat -> * gamma + beta -> relu
+(resnet50_dwt_mec_officehome.py:220-222,335-337): three module calls, two full-tensor
+concatenations, an affine pass and a ReLU pass.  ``DomainTripleNorm`` does the whole site in two
+kernel launches (statistics, apply) over the un-split tensor, the three domains batched on
+grid.z, gamma/beta/ReLU folded into the apply pass, and the running-statistic EMA applied
+source -> target -> target-aug in order so aliased buffers end exactly as after three
+sequential module calls.  Backward is likewise two launches and also yields
+dgamma/dbeta.
+
+It owns no state: it borrows the running buffers of the three domain modules at call time.
+"""
+from __future__ import annotations
+
+import torch.nn as nn
+
+from . import functional as F
+
+
+class DomainTripleNorm(nn.Module):
+    def __init__(self, kind, num_features, group_size=4, n_domains=3):
+        super().__init__()
+        if kind not in ("whiten", "bn"):
+            raise ValueError("kind must be 'whiten' or 'bn'")
+        self.kind, self.num_features, self.n_domains = kind, num_features, n_domains
+        self.group_size = min(num_features, group_size) if kind == "whiten" else 1
+        if self.group_size not in (1, 2, 4):
+            raise NotImplementedError("the fused site is built for group sizes 1, 2 and 4 "
+                                      f"(got {self.group_size}); use the per-domain modules")
+
+    def forward(self, x, domain_modules, gamma, beta, relu=False):
+        """x: [n_domains*N, C, H, W]; domain_modules: the per-domain WTransform2d / BatchNorm2d
+        modules (training mode), whose buffers receive the EMA updates; gamma/beta: [C,1,1]."""
+        mods = list(domain_modules)
+        if len(mods) != self.n_domains:
+            raise ValueError(f"expected {self.n_domains} domain modules")
+        if x.dim() != 4:
+            raise ValueError('expected 4D input (got {}D input)'.format(x.dim()))
+        m0 = mods[0]
+        if self.kind == "whiten":
+            running = [(m.running_mean, m.running_variance) for m in mods]
+            eps, momentum = m0.eps, m0.momentum
+        else:
+            for m in mods:
+                if m.training and m.track_running_stats:
+                    m.num_batches_tracked += 1
+            running = [(m.running_mean, m.running_var) for m in mods]
+            eps = m0.eps
+            momentum = m0.momentum if m0.momentum is not None else 1.0 / m0.num_batches_tracked.item()
+        update = m0.training and m0.track_running_stats
+        return F.norm(x, gamma, beta, kind=self.kind, group_size=self.group_size, n_domains=self.n_domains,
+                      training_stats=True, eps=eps, momentum=momentum, update_running=update,
+                      running=running, relu=relu)

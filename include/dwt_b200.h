@@ -1,0 +1,136 @@
+/*
+ * dwt_b200.h -- C ABI of the B200-native DWT hot path (libdwt_b200.so).
+ *
+ * Plain C, no torch types: raw device pointers, sizes, scalars, a caller-owned
+ * workspace and a CUDA stream.  Every entry point is stream-ordered, never
+ * synchronises the host, never allocates, and returns 0 on success or a negative
+ * DWT_E_* code (text through dwt_last_error()).  There is NO CPU path: the library
+ * only launches sm_100a kernels.
+ *
+ * What each entry point replaces in the reference (paths relative to
+ * /root/reference; the reference has no FFI -- its "plugin boundary" is Python
+ * module lookup by bare name, utils/ on sys.path, SURVEY.md §8b -- so these are
+ * the functions a ctypes shim behind the same nn.Module classes binds;
+ * INTEGRATION.md shows that binding):
+ *
+ *   dwt_whiten_fwd   _Whitening.forward            utils/whitening.py:37-61
+ *                    (+ the caller's shared gamma/beta/ReLU epilogue,
+ *                     resnet50_dwt_mec_officehome.py:59-63,220-222, when asked)
+ *   dwt_whiten_bwd   autograd through the above     utils/whitening.py:41-55
+ *   dwt_bn_fwd/bwd   _BatchNorm.forward             utils/batch_norm.py:54-69
+ *   dwt_mec_fwd_bwd  MinEntropyConsensusLoss.forward utils/consensus_loss.py:11-24
+ *
+ * Tensor layout: activations are fp32, contiguous [n_domains * N, C, HW]
+ * ("NCHW" with H*W flattened); domain d owns images [d*N, (d+1)*N).  The
+ * reference calls one module per domain (n_domains = 1); the fused domain-triple
+ * site passes n_domains = 3 in the order source | target | target-aug.
+ */
+#ifndef DWT_B200_H_
+#define DWT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DWT_B200_ABI_VERSION 1
+#define DWT_MAX_DOMAINS 4
+#define DWT_MAX_GROUP_SIZE 64
+
+/* error codes */
+#define DWT_OK 0
+#define DWT_E_INVALID (-1)     /* bad argument (shape, group size, null pointer)  */
+#define DWT_E_WORKSPACE (-2)   /* workspace too small / misaligned               */
+#define DWT_E_LAUNCH (-3)      /* CUDA launch or driver error                    */
+#define DWT_E_UNSUPPORTED (-4) /* valid in the reference, not built here         */
+
+/* mode */
+#define DWT_MODE_TRAIN 0 /* batch statistics (training, or track_running_stats=False) */
+#define DWT_MODE_EVAL 1  /* running statistics                                        */
+
+/* epilogue flags */
+#define DWT_EPI_NONE 0
+#define DWT_EPI_AFFINE 1 /* out = y * gamma[c] + beta[c]        */
+#define DWT_EPI_RELU 2   /* out = max(out, 0)  (needs AFFINE)   */
+
+typedef struct CUstream_st *dwt_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define DWT_API __attribute__((visibility("default")))
+#else
+#define DWT_API
+#endif
+
+DWT_API int dwt_abi_version(void);
+DWT_API const char *dwt_last_error(void);
+
+/* Workspace: one caller-owned device buffer, ZERO-FILLED once when allocated (the
+ * kernels keep their arrival counters self-resetting), reusable by any sequence of
+ * calls issued on ONE stream.  Size for the largest call the caller will make. */
+DWT_API size_t dwt_workspace_bytes(int64_t N, int64_t C, int64_t HW, int group_size, int n_domains);
+
+/* Device status word (first int of the workspace): 0 = ok, bit 0 = a covariance
+ * was not positive definite (the reference raises from torch.cholesky here).
+ * Read it with a device->host copy when you want to know; nothing syncs for it. */
+
+/*
+ * Whitening forward.
+ *   x, y            [n_domains*N, C, HW]
+ *   running_mean[d] [C]            (the reference's [1,C,1,1] buffer), may alias across d
+ *   running_cov[d]  [C/gs, gs, gs] ("running_variance"),               may alias across d
+ *   save_mean       [n_domains, C]            mean used (batch or running)
+ *   save_w          [n_domains, C/gs, gs, gs] W = inverse(cholesky((1-eps) cov + eps I))
+ *   gamma, beta     [C] or NULL (epilogue)
+ * TRAIN: batch mean/cov; when update_running, the EMA r = (1-m) r + m stat is applied
+ * domain by domain in order (so aliased buffers see s, then t, then t_aug --
+ * SURVEY.md H5), on the UN-shrunk covariance (whitening.py:57-59).
+ * EVAL: mean/cov come from the running buffers, nothing is written to them.
+ */
+DWT_API int dwt_whiten_fwd(const float *x, float *y, int64_t N, int64_t C, int64_t HW, int group_size,
+                   int n_domains, int mode, float eps, float momentum, int update_running,
+                   float *const *running_mean, float *const *running_cov, const float *gamma,
+                   const float *beta, int epilogue, float *save_mean, float *save_w,
+                   void *workspace, size_t workspace_bytes, dwt_stream_t stream);
+
+/*
+ * Whitening backward (closed form).  dout is the gradient of the
+ * forward's output (after the epilogue, if any).  dgamma/dbeta [C] are written
+ * (summed over domains) when the epilogue has AFFINE; pass NULL otherwise.
+ */
+DWT_API int dwt_whiten_bwd(const float *x, const float *dout, float *dx, int64_t N, int64_t C, int64_t HW,
+                   int group_size, int n_domains, int mode, float eps, const float *save_mean,
+                   const float *save_w, const float *gamma, const float *beta, int epilogue,
+                   float *dgamma, float *dbeta, void *workspace, size_t workspace_bytes,
+                   dwt_stream_t stream);
+
+/*
+ * Domain batch norm (F.batch_norm semantics): biased batch variance normalises,
+ * the UNBIASED one goes into running_var with weight `factor` (momentum, or
+ * 1/num_batches_tracked for the cumulative average, batch_norm.py:59-64).
+ *   weight, bias [C] or NULL ; save_mean, save_invstd [n_domains, C]
+ */
+DWT_API int dwt_bn_fwd(const float *x, float *y, int64_t N, int64_t C, int64_t HW, int n_domains, int mode,
+               float eps, float factor, int update_running, float *const *running_mean,
+               float *const *running_var, const float *weight, const float *bias, int epilogue,
+               float *save_mean, float *save_invstd, void *workspace, size_t workspace_bytes,
+               dwt_stream_t stream);
+
+DWT_API int dwt_bn_bwd(const float *x, const float *dout, float *dx, int64_t N, int64_t C, int64_t HW,
+               int n_domains, int mode, const float *save_mean, const float *save_invstd,
+               const float *weight, const float *bias, int epilogue, float *dweight, float *dbias,
+               void *workspace, size_t workspace_bytes, dwt_stream_t stream);
+
+/*
+ * Min-Entropy-Consensus loss, forward and both gradients in one launch.
+ *   x, y [N, K] logits;  loss [1];  gx, gy [N, K] = d loss / d x, d loss / d y.
+ * loss = mean_n min_k -(log_softmax(x) + log_softmax(y))[n,k] / 2
+ */
+DWT_API int dwt_mec_fwd_bwd(const float *x, const float *y, int64_t N, int64_t K, float *loss, float *gx,
+                    float *gy, dwt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DWT_B200_H_ */

@@ -1,0 +1,357 @@
+"""GPU parity: the CUDA path (through the drop-in modules -> ctypes -> C ABI) against
+  (1) golden outputs of the unmodified reference (tests/golden/*.npz), and
+  (2) the fp64 CPU oracle (oracle/dwt_oracle.py) on seeded inputs at sizes it finishes in seconds.
+
+Tolerance: BASELINE.json's bar is 1e-3 relative (fp32, norm-wise ||a-b||/||b||).  These tests
+assert TOL = 1e-3 on activations/gradients that pass through a Cholesky factor and TOL_STAT =
+1e-4 on plain statistics (means, covariances, running buffers, BN outputs).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import dwt_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+TOL_STAT = 1e-4
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+WHITEN = sorted(glob.glob(os.path.join(HERE, "w_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device("cuda", 0)
+
+
+def t(a, dev):
+    return torch.tensor(np.asarray(a), dtype=torch.float32, device=dev)
+
+
+def n(a):
+    return a.detach().double().cpu().numpy()
+
+
+# --------------------------------------------------------------------------- whitening
+@pytest.mark.parametrize("path", WHITEN, ids=[os.path.basename(p)[:-4] for p in WHITEN])
+def test_whitening_vs_reference_golden(path, dev):
+    import whitening                       # the drop-in shim -> dwt_b200.whitening
+    assert "dwt_b200" in whitening.WTransform2d.__module__
+    z = np.load(path)
+    gs, c = int(z["gs"]), z["x1"].shape[1]
+    m = whitening.WTransform2d(c, gs, running_m=t(z["rm0"], dev), running_var=t(z["rv0"], dev)).train()
+    x = t(z["x1"], dev).requires_grad_(True)
+    y = m(x)
+    (dx,) = torch.autograd.grad(y, x, t(z["dy"], dev))
+    assert rel_err(n(y), z["y1"]) < TOL
+    assert rel_err(n(dx), z["dx1"]) < TOL
+    assert rel_err(n(m.running_mean), z["rm1"]) < TOL_STAT and rel_err(n(m.running_variance), z["rv1"]) < TOL_STAT
+    with torch.no_grad():                                   # stats-collection forward
+        y2 = m(t(z["x2"], dev))
+    assert rel_err(n(y2), z["y2"]) < TOL
+    assert rel_err(n(m.running_mean), z["rm2"]) < TOL_STAT and rel_err(n(m.running_variance), z["rv2"]) < TOL_STAT
+    m.eval()
+    xe = t(z["x1"], dev).requires_grad_(True)
+    ye = m(xe)
+    (dxe,) = torch.autograd.grad(ye, xe, t(z["dy"], dev))
+    assert rel_err(n(ye), z["y_eval"]) < TOL and rel_err(n(dxe), z["dx_eval"]) < TOL
+    assert rel_err(n(m.running_mean), z["rm2"]) < TOL_STAT      # eval leaves the buffers alone
+    d = whitening.WTransform2d(c, gs).to(dev).train()           # default buffers: zeros / all-ones
+    with torch.no_grad():
+        d(t(z["x1"], dev))
+    assert rel_err(n(d.running_mean), z["rm_default1"]) < TOL_STAT
+    assert rel_err(n(d.running_variance), z["rv_default1"]) < TOL_STAT
+    from dwt_b200 import _native
+    assert _native.status(dev) == 0
+
+
+def _correlated(rng, nimg, c, h, w, offset=2.0):
+    z = rng.standard_normal((nimg, c, h, w))
+    mix = rng.standard_normal((c, c)) / np.sqrt(c) + np.eye(c)
+    return np.einsum("dc,nchw->ndhw", mix, z) + offset
+
+
+ORACLE_CASES = [   # N, C, H, W, gs
+    (8, 64, 56, 56, 4),       # ResNet layer1 site (per-domain slice, reduced N)
+    (4, 64, 112, 112, 4),     # ResNet stem site
+    (6, 256, 28, 28, 4),
+    (5, 32, 28, 28, 4),       # LeNet conv1 site
+    (16, 48, 14, 14, 4),      # LeNet conv2 site
+    (7, 24, 9, 9, 2),         # HW % 4 != 0 -> scalar path
+    (6, 128, 28, 28, 64),     # microbench group size
+    (12, 64, 20, 20, 32),
+    (9, 48, 10, 10, 16),
+    (5, 24, 7, 7, 8),         # tiled path, HW % 4 != 0
+    (6, 36, 8, 8, 12),        # group size not a power of two
+]
+
+
+@pytest.mark.parametrize("case", ORACLE_CASES, ids=lambda c: "n{}c{}h{}w{}g{}".format(*c))
+def test_whitening_vs_oracle_fp64(case, dev):
+    import whitening
+    nimg, c, h, w, gs = case
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    x, dy = _correlated(rng, nimg, c, h, w), rng.standard_normal((nimg, c, h, w))
+    rm0 = 0.1 * rng.standard_normal(c)
+    a = rng.standard_normal((c // gs, gs, gs))
+    rv0 = a @ a.transpose(0, 2, 1) / gs + 0.5 * np.eye(gs)
+    y_o, mean_o, w_o, rm1_o, rv1_o, cov_o = O.whiten_forward(x, gs, running_mean=rm0, running_cov=rv0)
+    dx_o = O.whiten_backward(x, dy, mean_o, w_o)
+    m = whitening.WTransform2d(c, gs, running_m=t(rm0.reshape(1, c, 1, 1), dev), running_var=t(rv0, dev)).train()
+    xt = t(x, dev).requires_grad_(True)
+    y = m(xt)
+    (dx,) = torch.autograd.grad(y, xt, t(dy, dev))
+    errs = dict(y=rel_err(n(y), y_o), dx=rel_err(n(dx), dx_o), rm=rel_err(n(m.running_mean).reshape(-1), rm1_o),
+                rv=rel_err(n(m.running_variance), rv1_o))
+    print(case, errs)
+    assert errs["y"] < TOL and errs["dx"] < TOL and errs["rm"] < TOL_STAT and errs["rv"] < TOL_STAT
+
+
+def test_whitening_large_mean_is_stable(dev):
+    """One-pass moments with a pilot shift: |mean| = 50 sigma must not cost accuracy."""
+    import whitening
+    rng = np.random.default_rng(5)
+    x = _correlated(rng, 6, 16, 12, 12, offset=0.0) * 0.2 + 10.0 + 40.0 * np.arange(16).reshape(1, 16, 1, 1) / 16
+    y_o, *_ = O.whiten_forward(x, 4)
+    m = whitening.WTransform2d(16, 4).to(dev).train()
+    assert rel_err(n(m(t(x, dev))), y_o) < TOL
+
+
+def test_whitening_errors(dev):
+    import whitening
+    with pytest.raises(ValueError, match="expected 4D input"):
+        whitening.WTransform2d(8, 4).to(dev)(torch.zeros(2, 8, 3, device=dev))
+    with pytest.raises(ValueError, match="divisible by group_size"):
+        whitening.WTransform2d(48, 32).to(dev)(torch.zeros(2, 48, 3, 3, device=dev))
+    from dwt_b200 import _native
+    with pytest.raises(_native.NativeError, match="no CPU fallback"):
+        whitening.WTransform2d(8, 4)(torch.zeros(2, 8, 3, 3))
+
+
+# --------------------------------------------------------------------------- batch norm
+@pytest.mark.parametrize("name", ["bn2d_affine", "bn2d_plain", "bn2d_hw4", "bn2d_cma", "bn1d_2", "bn1d_3", "bn3d"])
+def test_bn_vs_reference_golden(name, dev):
+    import batch_norm
+    z = np.load(os.path.join(HERE, "bn.npz"))
+    g = lambda k: z[f"{name}_{k}"]
+    cls = {"bn1d": batch_norm.BatchNorm1d, "bn2d": batch_norm.BatchNorm2d, "bn3d": batch_norm.BatchNorm3d}[name[:4]]
+    affine = f"{name}_weight" in z
+    mom = {"bn2d_cma": None, "bn3d": 0.3}.get(name, 0.1)
+    m = cls(g("x1").shape[1], t(g("rm0"), dev), t(g("rv0"), dev), affine=affine, momentum=mom).to(dev).train()
+    if affine:
+        with torch.no_grad():
+            m.weight.copy_(t(g("weight"), dev)); m.bias.copy_(t(g("bias"), dev))
+    x = t(g("x1"), dev).requires_grad_(True)
+    y = m(x)
+    y.backward(t(g("dy"), dev))
+    assert rel_err(n(y), g("y1")) < TOL_STAT and rel_err(n(x.grad), g("dx1")) < TOL_STAT
+    assert rel_err(n(m.running_mean), g("rm1")) < TOL_STAT and rel_err(n(m.running_var), g("rv1")) < TOL_STAT
+    if affine:
+        assert rel_err(n(m.weight.grad), g("dweight")) < TOL_STAT and rel_err(n(m.bias.grad), g("dbias")) < TOL_STAT
+    with torch.no_grad():
+        m(t(g("x2"), dev))
+    assert rel_err(n(m.running_mean), g("rm2")) < TOL_STAT and rel_err(n(m.running_var), g("rv2")) < TOL_STAT
+    assert int(m.num_batches_tracked) == int(g("nbt2"))
+    m.eval()
+    xe = t(g("x1"), dev).requires_grad_(True)
+    ye = m(xe)
+    ye.backward(t(g("dy"), dev))
+    assert rel_err(n(ye), g("y_eval")) < TOL_STAT and rel_err(n(xe.grad), g("dx_eval")) < TOL_STAT
+
+
+@pytest.mark.parametrize("shape", [(8, 512, 7, 7), (6, 128, 28, 28), (4, 2048, 7, 7), (5, 256, 14, 14)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_bn_vs_oracle_fp64(shape, dev):
+    import batch_norm
+    rng = np.random.default_rng(3)
+    c = shape[1]
+    x = rng.standard_normal(shape) * (0.5 + rng.random((1, c, 1, 1))) + rng.standard_normal((1, c, 1, 1))
+    dy = rng.standard_normal(shape)
+    rm0, rv0 = 0.1 * rng.standard_normal(c), 0.5 + rng.random(c)
+    y_o, mean_o, inv_o, rm1_o, rv1_o = O.bn_forward(x, rm0, rv0)
+    dx_o, _, _ = O.bn_backward(x, dy, mean_o, inv_o)
+    m = batch_norm.BatchNorm2d(c, t(rm0, dev), t(rv0, dev), affine=False).train()
+    xt = t(x, dev).requires_grad_(True)
+    y = m(xt)
+    y.backward(t(dy, dev))
+    assert rel_err(n(y), y_o) < TOL_STAT and rel_err(n(xt.grad), dx_o) < TOL_STAT
+    assert rel_err(n(m.running_mean), rm1_o) < TOL_STAT and rel_err(n(m.running_var), rv1_o) < TOL_STAT
+
+
+# --------------------------------------------------------------------------- MEC
+@pytest.mark.parametrize("name", ["plain", "big", "k10", "n1", "ties"])
+def test_mec_vs_reference_golden(name, dev):
+    import consensus_loss
+    z = np.load(os.path.join(HERE, "mec.npz"))
+    x, y = t(z[name + "_x"], dev).requires_grad_(True), t(z[name + "_y"], dev).requires_grad_(True)
+    crit = consensus_loss.MinEntropyConsensusLoss(num_classes=x.shape[1], device=dev)
+    loss = crit(x, y)
+    assert loss.dim() == 0
+    (0.7 * loss).backward()
+    assert abs(float(loss) - float(z[name + "_loss"])) < 1e-5 * max(1.0, abs(float(loss)))
+    assert rel_err(n(x.grad), 0.7 * z[name + "_gx"]) < TOL_STAT and rel_err(n(y.grad), 0.7 * z[name + "_gy"]) < TOL_STAT
+
+
+def test_mec_vs_oracle_batch64(dev):
+    import consensus_loss
+    rng = np.random.default_rng(9)
+    x, y = 3 * rng.standard_normal((64, 65)), 3 * rng.standard_normal((64, 65))
+    loss_o, gx_o, gy_o, _ = O.mec_loss(x, y)
+    xt, yt = t(x, dev).requires_grad_(True), t(y, dev).requires_grad_(True)
+    loss = consensus_loss.MinEntropyConsensusLoss(65, dev)(xt, yt)
+    loss.backward()
+    assert abs(float(loss) - loss_o) < 1e-5 and rel_err(n(xt.grad), gx_o) < TOL_STAT and rel_err(n(yt.grad), gy_o) < TOL_STAT
+
+
+# --------------------------------------------------------------------------- fused domain triple
+@pytest.mark.parametrize("kind,c,hw,gs", [("whiten", 64, 28, 4), ("whiten", 256, 14, 4), ("bn", 128, 14, 1),
+                                           ("bn", 512, 7, 1), ("whiten", 16, 9, 2)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_fused_triple_vs_oracle(kind, c, hw, gs, relu, dev):
+    """DomainTripleNorm == split/3 -> 3 modules on ALIASED buffers -> cat -> *gamma+beta -> relu
+    (resnet50_dwt_mec_officehome.py:220-222), incl. the sequential EMA of SURVEY.md H5."""
+    import batch_norm
+    import whitening
+    from dwt_b200 import DomainTripleNorm
+    rng = np.random.default_rng(11)
+    nper = 5
+    x = np.concatenate([_correlated(rng, nper, c, hw, hw, offset=o) for o in (0.5, -1.0, 2.0)])
+    dout = rng.standard_normal(x.shape)
+    gamma, beta = 0.5 + rng.random(c), 0.3 * rng.standard_normal(c)
+    if kind == "whiten":
+        rm = 0.1 * rng.standard_normal(c)
+        a = rng.standard_normal((c // gs, gs, gs))
+        rv = a @ a.transpose(0, 2, 1) / gs + 0.5 * np.eye(gs)
+    else:
+        rm, rv = 0.1 * rng.standard_normal(c), 0.5 + rng.random(c)
+    # oracle: three sequential domain calls on the same buffers
+    outs, dxs = [], []
+    dgamma, dbeta = np.zeros(c), np.zeros(c)
+    rm_o, rv_o = rm, rv
+    for d in range(3):
+        xd, dd = x[d * nper:(d + 1) * nper], dout[d * nper:(d + 1) * nper]
+        if kind == "whiten":
+            y, mean, w, rm_o, rv_o, _ = O.whiten_forward(xd, gs, running_mean=rm_o, running_cov=rv_o)
+        else:
+            y, mean, inv, rm_o, rv_o = O.bn_forward(xd, rm_o, rv_o)
+        pre = O.scale_shift_relu(y, gamma, beta, False)
+        out = np.maximum(pre, 0) if relu else pre
+        dz = dd * (pre > 0) if relu else dd
+        dgamma += (dz * y).sum(axis=(0, 2, 3)); dbeta += dz.sum(axis=(0, 2, 3))
+        dyd = dz * gamma.reshape(1, c, 1, 1)
+        dxs.append(O.whiten_backward(xd, dyd, mean, w) if kind == "whiten" else O.bn_backward(xd, dyd, mean, inv)[0])
+        outs.append(out)
+    rm_t = t(rm.reshape(1, c, 1, 1) if kind == "whiten" else rm, dev)
+    rv_t = t(rv, dev)
+    if kind == "whiten":
+        mods = [whitening.WTransform2d(c, gs, running_m=rm_t, running_var=rv_t).train() for _ in range(3)]
+    else:
+        mods = [batch_norm.BatchNorm2d(c, rm_t, rv_t, affine=False).train() for _ in range(3)]
+    site = DomainTripleNorm(kind, c, gs)
+    g_t = t(gamma.reshape(c, 1, 1), dev).requires_grad_(True)
+    b_t = t(beta.reshape(c, 1, 1), dev).requires_grad_(True)
+    xt = t(x, dev).requires_grad_(True)
+    out = site(xt, mods, g_t, b_t, relu=relu)
+    out.backward(t(dout, dev))
+    tol = TOL if kind == "whiten" else TOL_STAT
+    assert rel_err(n(out), np.concatenate(outs)) < tol
+    assert rel_err(n(xt.grad), np.concatenate(dxs)) < tol
+    assert rel_err(n(g_t.grad).reshape(-1), dgamma) < tol and rel_err(n(b_t.grad).reshape(-1), dbeta) < tol
+    assert rel_err(n(rm_t).reshape(-1), rm_o) < TOL_STAT and rel_err(n(rv_t), rv_o) < TOL_STAT
+    if kind == "bn":
+        assert all(int(m.num_batches_tracked) == 1 for m in mods)
+
+
+# --------------------------------------------------------------------------- full-size properties
+def test_microbench_shape_properties(dev):
+    """BASELINE.json config 2 at full size (N=256,C=256,56x56,gs=64): size-independent properties
+    instead of a CPU oracle.  With S = (1-eps) Sigma + eps I = L L^T and W = L^-1:
+        mean(y) = 0,   (1-eps) cov(y) + eps W W^T = I,   y == fp64 recomputation on the device,
+        <dy, J v> == <J^T dy, v> (J v by central differences of the layer itself), sum_m dx = 0."""
+    import whitening
+    torch.manual_seed(0)
+    N, C, H, gs, eps = 256, 256, 56, 64, 1e-3
+    mix = torch.randn(C, C, device=dev) / C ** 0.5 + torch.eye(C, device=dev)
+    x = torch.einsum("dc,nchw->ndhw", mix, torch.randn(N, C, H, H, device=dev)) + 2.0
+    m = whitening.WTransform2d(C, gs).to(dev).train()
+    x.requires_grad_(True)
+    y = m(x)
+    G = C // gs
+    yg = y.detach().transpose(0, 1).reshape(G, gs, -1).double()
+    mean_y = yg.mean(-1)
+    cov_y = yg @ yg.transpose(1, 2) / yg.shape[-1]
+    assert mean_y.abs().max() < 1e-4
+    xg = x.detach().transpose(0, 1).reshape(G, gs, -1).double()
+    xc = xg - xg.mean(-1, keepdim=True)
+    sigma = xc @ xc.transpose(1, 2) / xc.shape[-1]
+    S = (1 - eps) * sigma + eps * torch.eye(gs, device=dev, dtype=torch.float64)
+    W_ref = torch.linalg.inv(torch.linalg.cholesky(S))
+    y_ref = (W_ref @ xc).reshape(C, N, H, H).transpose(0, 1)
+    assert rel_err(n(y), n(y_ref)) < TOL
+    ident = (1 - eps) * cov_y + eps * (W_ref @ W_ref.transpose(1, 2))
+    assert (ident - torch.eye(gs, device=dev, dtype=torch.float64)).abs().max() < 1e-3
+    dy = torch.randn_like(y)
+    (dx,) = torch.autograd.grad(y, x, dy)
+    # adjoint test: directional derivative by central differences of the layer itself vs <dx, v>
+    v = torch.randn_like(x)
+    h = 1e-2
+    with torch.no_grad():
+        jv = (m(x + h * v) - m(x - h * v)) / (2 * h)
+    lhs, rhs = (dy.double() * jv.double()).sum().item(), (dx.double() * v.double()).sum().item()
+    assert abs(lhs - rhs) < 2e-3 * max(abs(lhs), abs(rhs), 1.0)
+    assert dx.sum(dim=(0, 2, 3)).abs().max() < 1e-2 * dx.abs().sum(dim=(0, 2, 3)).max()   # gradient of a centred map
+
+
+def test_resnet_site_fullsize_idempotence(dev):
+    """ResNet stem site at the benchmark size (64 images/domain, 64x112x112, gs=4): whitening an
+    already whitened batch is (up to the eps shrink) the identity -- W' ~ I / sqrt((1-eps)/(1-eps) ...)."""
+    import whitening
+    torch.manual_seed(1)
+    x = torch.randn(64, 64, 112, 112, device=dev) * 3 + 1
+    m = whitening.WTransform2d(64, 4).to(dev).train()
+    with torch.no_grad():
+        y = m(x)
+        y2 = m(y)
+    # cov(y) = (I - eps W W^T)/(1-eps); second pass sees S2 = I - eps W W^T + eps I, whose Cholesky inverse is
+    # within O(eps * ||W W^T - I||) of I.  For this well-conditioned input (var 9): W W^T ~ I/9.
+    assert rel_err(n(y2[:4]), n(y[:4])) < 2e-3
+    assert y.mean(dim=(0, 2, 3)).abs().max() < 1e-4
+
+
+# --------------------------------------------------------------------------- full model
+@pytest.mark.parametrize("site_mode", ["modules", "fused"])
+def test_resnet_tiny_vs_reference_golden(site_mode, dev):
+    """The harness model with the CUDA layers vs the unmodified reference ResNet (CPU, fp32) on the
+    same synthetic checkpoint and batch: logits, losses, selected gradients, buffers."""
+    import torch.nn.functional as Fn
+    import dwt_b200
+    from harness.resnet50_dwt import build_resnet50_dwt
+    from harness.synth import synth_batch, synth_state_dict
+    z = np.load(os.path.join(HERE, "resnet_tiny.npz"))
+    sd = {k: v.to(dev) for k, v in synth_state_dict(seed=1).items()}
+    x, labels = synth_batch(seed=2, per_domain=2, size=64)
+    model = build_resnet50_dwt(sd, dwt_b200, site_mode=site_mode).to(dev).train()
+    logits = model(x.to(dev))
+    s, tt, a = torch.split(logits, logits.shape[0] // 3, dim=0)
+    cls = Fn.nll_loss(Fn.log_softmax(s, dim=1), labels.to(dev))
+    mec = 0.1 * dwt_b200.MinEntropyConsensusLoss(65, dev)(tt, a)
+    (cls + mec).backward()
+    assert rel_err(n(logits), z["logits"]) < 5e-3          # 53 norm sites deep; per-layer bar is 1e-3
+    assert abs(float(cls) - float(z["cls_loss"])) < 5e-3 and abs(float(mec) - float(z["mec_loss"])) < 5e-3
+    params = dict(model.named_parameters())
+    for k in [k[5:] for k in z.files if k.startswith("grad/")]:
+        assert rel_err(n(params[k].grad), z["grad/" + k]) < 2e-2, k
+    bufs = model.state_dict()
+    for k in [k[4:] for k in z.files if k.startswith("buf/")]:
+        assert rel_err(n(bufs[k]), z["buf/" + k]) < 1e-3, k
+    model.eval()
+    with torch.no_grad():
+        assert rel_err(n(model(x.to(dev))), z["logits_eval"]) < 5e-3
