@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- ResNet-50-DWT training-step throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload resnet|microbench] [--per-domain B] [--site-mode fused|modules]
+
+One "step" = one full training step of the ResNet-50-DWT harness model (harness/resnet50_dwt.py,
+the reference topology with this repo's CUDA layers dropped in) on one synthetic Office-Home-shaped
+batch: B source + B target + B target-aug images of 3x224x224 (B = 64 per domain -> 192 images per
+GPU), forward, NLL(source) + 0.1 * MEC(target, target-aug), backward, SGD(momentum)
+update.  N > 1: one process per GPU (torchrun), plain data parallel, gradients all-reduced by NCCL
+(DistributedDataParallel, rank-local whitening statistics, buffers not broadcast).
+
+Prints ONE JSON line on rank 0 (see the task contract): `value` = images/s with inputs resident in
+HBM; `e2e` = images/s through the same public call with the step's images copied from pinned host
+memory and the loss read back inside the timed region; `roofline` = the dominant hand-written
+kernel family against the measured HBM peak; `cpu_baseline` = the CPU port of the reference
+layers (oracle/torch_port.py, same harness model) timed on this box's host cores.
+
+--impl reference: the reference's own CPU path (no GPU): the same step with the reference's
+operator sequence on stock ATen CPU ops (oracle/torch_port.py), all host threads, a bounded sample.
+--workload microbench: BASELINE.json configs[1] (WTransform2d N=256 C=256 56x56 gs=64 fwd+bwd).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PLUGIN_DIR = os.path.join(ROOT, "dwt-domain-adaptation_b200")
+for _p in (PLUGIN_DIR, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch                                     # noqa: E402
+import torch.nn.functional as F                  # noqa: E402
+
+LAMBDA_MEC = 0.1                                 # resnet50_dwt_mec_officehome.py:508
+NUM_CLASSES = 65
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- model
+def build_model(layers, device, site_mode, seed=1):
+    from harness.resnet50_dwt import build_resnet50_dwt
+    from harness.synth import synth_state_dict
+    sd = {k: v.to(device) for k, v in synth_state_dict(seed=seed).items()}
+    model = build_resnet50_dwt(sd, layers, site_mode=site_mode).to(device)
+    return model.train()
+
+
+def make_optimizer(model):
+    """SGD with the reference's two parameter groups (resnet50_dwt_mec_officehome.py:578-590)."""
+    head = [p for n, p in model.named_parameters() if n.startswith("fc_out")]
+    body = [p for n, p in model.named_parameters() if not n.startswith("fc_out")]
+    return torch.optim.SGD([{"params": body, "lr": 1e-3}, {"params": head, "lr": 1e-2}], momentum=0.9,
+                           weight_decay=5e-4)
+
+
+def train_step(model, mec, opt, images, labels):
+    opt.zero_grad(set_to_none=True)
+    logits = model(images)
+    src, tgt, aug = torch.split(logits, logits.shape[0] // 3, dim=0)
+    loss = F.nll_loss(F.log_softmax(src, dim=1), labels) + LAMBDA_MEC * mec(tgt, aug)
+    loss.backward()
+    opt.step()
+    return loss
+
+
+# ----------------------------------------------------------------------------------------- arms
+def run_reference(args):
+    """The reference's CPU path: harness model + CPU port of the reference layers, all host threads."""
+    import oracle.torch_port as port
+    from harness.synth import synth_batch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    per_domain = args.cpu_per_domain
+    dev = torch.device("cpu")
+    model = build_model(port, dev, "modules")
+    opt = make_optimizer(model)
+    mec = port.MinEntropyConsensusLoss(NUM_CLASSES, dev)
+    images, labels = synth_batch(seed=2, per_domain=per_domain)
+    for _ in range(args.warmup):
+        train_step(model, mec, opt, images, labels)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        train_step(model, mec, opt, images, labels)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = 3 * per_domain / dt
+    sample = f"{args.steps} steps of {3 * per_domain} images (3x{per_domain}), same model/step as the GPU arm"
+    print(json.dumps({
+        "impl": "reference", "metric": "ResNet-50-DWT images/sec fwd+bwd", "value": val, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, per_domain=per_domain, site_mode="modules"),
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, per_domain, site_mode):
+    return {"workload": "ResNet-50-DWT synthetic Office-Home 224x224, train step = fwd + NLL + 0.1*MEC + bwd + SGD",
+            "per_domain_batch": per_domain, "images_per_gpu": 3 * per_domain, "global_images": 3 * per_domain * args.gpus,
+            "group_size": 4, "site_mode": site_mode, "parallelism": f"dp{args.gpus}",
+            "l2": "no explicit flush: per-step working set (activations) is tens of GB >> 126 MB L2"}
+
+
+def cpu_baseline(args):
+    """Bounded CPU sample on rank 0: a few steps of the CPU port at a small per-domain batch."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--cpu-per-domain", str(args.cpu_per_domain)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="0", WORLD_SIZE="1")
+    for k in ("LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600).stdout.strip().splitlines()
+        return json.loads(out[-1])["cpu_baseline"]
+    except Exception as e:                                   # the GPU number must not die with the CPU leg
+        return {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+
+
+def timed_loop(step_fn, steps, device, distributed):
+    import torch.distributed as dist
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if distributed:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import dwt_b200
+    from dwt_b200 import _native
+    from harness.synth import synth_batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if distributed:
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.backends.cudnn.benchmark = True
+    _native.lib()                                           # fail loudly if the extension is missing
+
+    if args.workload == "microbench":
+        return run_microbench(args, device, rank)
+
+    model = build_model(dwt_b200, device, args.site_mode)
+    net = model
+    if distributed:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
+                                                        gradient_as_bucket_view=True)
+    opt = make_optimizer(model)
+    mec = dwt_b200.MinEntropyConsensusLoss(NUM_CLASSES, device)
+    B = args.per_domain
+    host_images, host_labels = synth_batch(seed=100 + rank, per_domain=B)
+    host_images, host_labels = host_images.pin_memory(), host_labels.pin_memory()
+    images, labels = host_images.to(device), host_labels.to(device)
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        train_step(net, mec, opt, images, labels)
+
+    def step_e2e():
+        im = host_images.to(device, non_blocking=True)
+        lb = host_labels.to(device, non_blocking=True)
+        loss = train_step(net, mec, opt, im, lb)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()     # the user reads the loss every step
+
+    for _ in range(args.warmup):
+        step_resident()
+    n0 = _native.launch_count()
+    with ClockSampler(local) as clocks:
+        _native.profile_begin()
+        ms = timed_loop(step_resident, args.steps, device, distributed)
+        prof = _native.profile_end()
+    launches = (_native.launch_count() - n0) // args.steps
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed_loop(step_e2e, args.steps, device, distributed)
+
+    per_gpu = 3 * B
+    value = per_gpu * world * args.steps / (ms / 1e3)
+    e2e = per_gpu * world * args.steps / (ms_e2e / 1e3)
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    fams = {k: dict(v, gbs=(v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None),
+                    us_per_launch=(1e3 * v["ms"] / v["launches"] if v["launches"] else None),
+                    share_of_step=v["ms"] / ms) for k, v in prof.items()}
+    dom = max((k for k in fams if fams[k]["bytes"] > 0), key=lambda k: fams[k]["ms"], default=None)
+    roof = None
+    if dom is not None:
+        f = fams[dom]
+        roof = {"bound": "hbm", "kernel": dom, "achieved": f["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": f["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "launches_timed": f["launches"], "avg_launch_us": f["us_per_launch"],
+                "algorithmic_bytes_per_launch": f["bytes"] / f["launches"],
+                "all_norm_kernels_share_of_step": sum(v["ms"] for v in fams.values()) / ms}
+    out = {
+        "metric": "ResNet-50-DWT images/sec fwd+bwd", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, per_domain=B, site_mode=args.site_mode),
+        "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": host_images.numel() * 4 + host_labels.numel() * 8, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "kernels": fams,
+        "conv_math": "cuDNN, TF32 allowed (torch default) -- convolutions are not part of the hot path",
+    }
+    if args.cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(out))
+    if distributed:
+        dist.destroy_process_group()
+
+
+def run_microbench(args, device, rank):
+    """BASELINE.json configs[1]: WTransform2d N=256 C=256 H=W=56 group_size=64, fwd+bwd."""
+    import dwt_b200
+    from dwt_b200 import _native
+    N, C, H, gs = args.micro_n, 256, 56, args.micro_gs
+    torch.manual_seed(0)
+    mix = torch.randn(C, C, device=device) / C ** 0.5 + torch.eye(C, device=device)
+    x = (torch.einsum("dc,nchw->ndhw", mix, torch.randn(N, C, H, H, device=device)) + 2.0).requires_grad_(True)
+    dy = torch.randn(N, C, H, H, device=device)
+    m = dwt_b200.WTransform2d(C, gs).to(device).train()
+
+    def step():
+        y = m(x)
+        torch.autograd.grad(y, x, dy)
+
+    for _ in range(args.warmup):
+        step()
+    with ClockSampler(device.index) as clocks:
+        _native.profile_begin()
+        ms = timed_loop(step, args.steps, device, False)
+        prof = _native.profile_end()
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    elems = N * C * H * H
+    total_bytes = 32.0 * elems                       # 12 B/elem forward + 20 B/elem backward
+    fams = {k: dict(v, gbs=v["bytes"] / (v["ms"] * 1e-3) / 1e9, us_per_launch=1e3 * v["ms"] / v["launches"])
+            for k, v in prof.items() if v["ms"] > 0}
+    gbs = total_bytes * args.steps / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "WTransform2d fwd+bwd microbench", "value": args.steps / (ms * 1e-3), "unit": "iterations/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"WTransform2d N={N} C={C} H=W={H} group_size={gs} fwd+bwd",
+                   "l2": f"tensor of {elems * 4 / 1e6:.0f} MB > 126 MB L2"},
+        "roofline": {"bound": "hbm", "kernel": "fwd+bwd (4 launches)", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                     "frac": gbs / peak, "traffic": None, "peak_source": peak_src},
+        "kernels": fams, "clocks": clocks.summary(),
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=["resnet", "microbench"], default="resnet")
+    ap.add_argument("--per-domain", type=int, default=64)
+    ap.add_argument("--site-mode", choices=["fused", "modules"], default="fused")
+    ap.add_argument("--cpu-per-domain", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--micro-n", type=int, default=256)
+    ap.add_argument("--micro-gs", type=int, default=64)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

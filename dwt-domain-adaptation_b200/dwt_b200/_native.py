@@ -46,7 +46,30 @@ _SIGNATURES = {
                                   ctypes.c_void_p]),
     "dwt_mec_fwd_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, _c_float_p,
                                        _c_float_p, _c_float_p, ctypes.c_void_p]),
+    "dwt_launch_count": (ctypes.c_int64, []),
+    "dwt_profile_begin": (None, []),
+    "dwt_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
 }
+
+
+class ProfileEntry(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 48), ("launches", ctypes.c_int64), ("ms", ctypes.c_double),
+                ("bytes", ctypes.c_double)]
+
+
+def profile_begin():
+    lib().dwt_profile_begin()
+
+
+def profile_end():
+    """-> {kernel family: dict(launches, ms, bytes)}; waits for the recorded events."""
+    buf = (ProfileEntry * 32)()
+    k = lib().dwt_profile_end(ctypes.cast(buf, ctypes.c_void_p), 32)
+    return {buf[i].name.decode(): dict(launches=buf[i].launches, ms=buf[i].ms, bytes=buf[i].bytes) for i in range(k)}
+
+
+def launch_count() -> int:
+    return int(lib().dwt_launch_count())
 EXPORTS = tuple(_SIGNATURES)
 
 _lib = None
@@ -125,7 +148,7 @@ def workspace(device, n, c, hw, gs, nd):
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < need:
-        buf = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        buf = torch.zeros(max(need, 8 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
     return buf
 

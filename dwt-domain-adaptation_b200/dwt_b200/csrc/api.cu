@@ -4,7 +4,11 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
+#include <string>
+#include <vector>
+#include <string.h>
 
 #include "norm_launch.h"
 
@@ -40,6 +44,40 @@ int sm_count() {
   return n;
 }
 
+// ---- launch accounting / optional per-kernel event timing ------------------------------------
+std::atomic<int64_t> g_launches{0};
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+struct ProfRec { const char* name; cudaEvent_t a, b; double bytes; };
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// RAII bracket around one kernel launch
+struct Launch {
+  cudaStream_t st; ProfRec rec; bool on;
+  Launch(const char* name, double bytes, cudaStream_t s) : st(s), rec{name, nullptr, nullptr, bytes}, on(false) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof_on && g_prof.size() < (1u << 18)) {
+      on = true; rec.a = take_event(); rec.b = take_event();
+      cudaEventRecord(rec.a, st);
+    }
+  }
+  ~Launch() {
+    if (!on) return;
+    cudaEventRecord(rec.b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(rec);
+  }
+};
+
 std::once_flag g_tiled_once;
 int g_tiled_rc = 0;
 int ensure_tiled() {
@@ -69,17 +107,26 @@ struct Workspace {
   size_t bytes;
 };
 
+// The head of the workspace holds ONLY the status word and the arrival counters, at offsets
+// that do not depend on the geometry: every call leaves its counters at zero, so calls with
+// different shapes can share one zero-initialised buffer.  Scratch (any content) follows.
+constexpr size_t kMaxGroups = 65536;
+constexpr size_t kOffCounters = 256;
+constexpr size_t kOffDom1 = kOffCounters + sizeof(int) * DWT_MAX_DOMAINS * kMaxGroups;
+constexpr size_t kOffDom2 = kOffDom1 + sizeof(int) * kMaxGroups;
+constexpr size_t kOffScratch = kOffDom2 + sizeof(int) * kMaxGroups;
+
 Workspace carve(void* base, int64_t C, int GS, int D) {
   const int G = (int)(C / GS);
   const int cap = chunk_cap(GS, G, D);
-  size_t off = 0;
+  size_t off = kOffScratch;
   auto take = [&](size_t nbytes) { size_t o = off; off = align_up(off + nbytes, 256); return o; };
   char* b = static_cast<char*>(base);
   Workspace w;
-  w.status = reinterpret_cast<int*>(b + take(sizeof(int)));
-  w.counters = reinterpret_cast<int*>(b + take(sizeof(int) * (size_t)D * G));
-  w.dom_counter = reinterpret_cast<int*>(b + take(sizeof(int) * (size_t)G));
-  w.dom_counter2 = reinterpret_cast<int*>(b + take(sizeof(int) * (size_t)G));
+  w.status = reinterpret_cast<int*>(b);
+  w.counters = reinterpret_cast<int*>(b + kOffCounters);
+  w.dom_counter = reinterpret_cast<int*>(b + kOffDom1);
+  w.dom_counter2 = reinterpret_cast<int*>(b + kOffDom2);
   w.partial = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * cap * (GS * GS + GS)));
   w.save_cov = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * GS * GS));
   w.coef = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * dwt::coef_stride(GS)));
@@ -152,16 +199,22 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
   for (int d = 0; d < D; ++d) { fin.rmean[d] = need_running ? rmean[d] : nullptr; fin.rcov[d] = need_running ? rcov[d] : nullptr; }
   fin.dom_counter = w.dom_counter; fin.status = w.status;
 
+  const double E = 4.0 * (double)D * (double)N * (double)C * (double)HW;   // bytes of one activation tensor
   if (mode == DWT_MODE_TRAIN) {
+    Launch l(p.small ? "small_stats" : "tiled_stats", E, st);
     if (p.small) dwt::small_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
     else dwt::tiled_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
   } else {
+    Launch l("eval_prep", 0.0, st);
     if (p.small) dwt::small_eval_prep(p.gm, fin, st);
     else dwt::tiled_eval_prep(p.gm, fin, st);
   }
   if (int rc = check_launch("whitening statistics kernel")) return rc;
-  if (p.small) dwt::small_apply(x, y, p.gm, p.vec, p.chunks_ew, epi, save_mean, save_w, gamma, beta, st);
-  else dwt::tiled_apply(x, y, p.gm, p.vec, p.chunks_ew, save_mean, save_w, st);
+  {
+    Launch l(p.small ? "small_apply" : "tiled_apply", 2 * E, st);
+    if (p.small) dwt::small_apply(x, y, p.gm, p.vec, p.chunks_ew, epi, save_mean, save_w, gamma, beta, st);
+    else dwt::tiled_apply(x, y, p.gm, p.vec, p.chunks_ew, save_mean, save_w, st);
+  }
   return check_launch("whitening apply kernel");
 }
 
@@ -192,16 +245,22 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
   fin.dom_counter = w.dom_counter2;
 
   const bool need_reduce = (mode == DWT_MODE_TRAIN) || (fin.dgamma != nullptr);
+  const double E = 4.0 * (double)D * (double)N * (double)C * (double)HW;
   if (need_reduce) {
+    Launch l(p.small ? "small_bwd_reduce" : "tiled_bwd_reduce", 2 * E, st);
     if (p.small) dwt::small_bwd_reduce(x, dout, p.gm, p.vec, fin, beta, w.partial, w.counters, st);
     else dwt::tiled_bwd_reduce(x, dout, p.gm, p.vec, fin, w.partial, w.counters, st);
   } else {
+    Launch l("bwd_prep", 0.0, st);
     if (p.small) dwt::small_bwd_prep(p.gm, fin, st);
     else dwt::tiled_bwd_prep(p.gm, fin, st);
   }
   if (int rc = check_launch("whitening backward reduction kernel")) return rc;
-  if (p.small) dwt::small_bwd_apply(x, dout, dx, p.gm, p.vec, p.chunks_ew, epi, w.coef, save_mean, save_w, gamma, beta, st);
-  else dwt::tiled_bwd_apply(x, dout, dx, p.gm, p.vec, p.chunks_ew, w.coef, st);
+  {
+    Launch l(p.small ? "small_bwd_apply" : "tiled_bwd_apply", 3 * E, st);
+    if (p.small) dwt::small_bwd_apply(x, dout, dx, p.gm, p.vec, p.chunks_ew, epi, w.coef, save_mean, save_w, gamma, beta, st);
+    else dwt::tiled_bwd_apply(x, dout, dx, p.gm, p.vec, p.chunks_ew, w.coef, st);
+  }
   return check_launch("whitening backward apply kernel");
 }
 
@@ -263,8 +322,47 @@ int dwt_mec_fwd_bwd(const float* x, const float* y, int64_t N, int64_t K, float*
                     dwt_stream_t stream) {
   if (!x || !y || !loss || !gx || !gy) return fail(DWT_E_INVALID, "null pointer argument");
   if (N <= 0 || K <= 0 || N >= (1 << 24) || K >= (1 << 24)) return fail(DWT_E_INVALID, "bad logits shape [%lld,%lld]", (long long)N, (long long)K);
-  dwt::mec_launch(x, y, (int)N, (int)K, loss, gx, gy, (cudaStream_t)stream);
+  {
+    Launch l("mec", 16.0 * (double)N * (double)K, (cudaStream_t)stream);
+    dwt::mec_launch(x, y, (int)N, (int)K, loss, gx, gy, (cudaStream_t)stream);
+  }
   return check_launch("MEC kernel");
+}
+
+int64_t dwt_launch_count(void) { return g_launches.load(); }
+
+void dwt_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { g_event_pool.push_back(r.a); g_event_pool.push_back(r.b); }
+  g_prof.clear();
+  g_prof_on = true;
+}
+
+int dwt_profile_end(dwt_profile_entry* out, int max_entries) {
+  std::vector<ProfRec> recs;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = false;
+    recs.swap(g_prof);
+  }
+  int n = 0;
+  for (auto& r : recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      int k = 0;
+      for (; k < n; ++k)
+        if (strcmp(out[k].name, r.name) == 0) break;
+      if (k == n && n < max_entries) {
+        memset(&out[n], 0, sizeof(out[n]));
+        strncpy(out[n].name, r.name, sizeof(out[n].name) - 1);
+        ++n;
+      }
+      if (k < n) { out[k].launches += 1; out[k].ms += ms; out[k].bytes += r.bytes; }
+    }
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_event_pool.push_back(r.a); g_event_pool.push_back(r.b);
+  }
+  return n;
 }
 
 }  // extern "C"

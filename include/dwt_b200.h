@@ -130,6 +130,24 @@ DWT_API int dwt_bn_bwd(const float *x, const float *dout, float *dx, int64_t N, 
 DWT_API int dwt_mec_fwd_bwd(const float *x, const float *y, int64_t N, int64_t K, float *loss, float *gx,
                     float *gy, dwt_stream_t stream);
 
+/*
+ * Measurement hooks (used by bench.py; not part of the reference's surface).
+ * dwt_launch_count: kernels launched by this library since it was loaded.
+ * dwt_profile_begin/end: while enabled, every kernel launch is bracketed by CUDA events on
+ * its own stream; dwt_profile_end waits for them and returns one entry per kernel family with
+ * the launch count, the summed device time and the summed ALGORITHMIC bytes.
+ */
+typedef struct {
+  char name[48];
+  int64_t launches;
+  double ms;
+  double bytes;
+} dwt_profile_entry;
+
+DWT_API int64_t dwt_launch_count(void);
+DWT_API void dwt_profile_begin(void);
+DWT_API int dwt_profile_end(dwt_profile_entry *out, int max_entries);
+
 #ifdef __cplusplus
 }
 #endif

@@ -196,7 +196,7 @@ def test_mec_vs_reference_golden(name, dev):
     loss = crit(x, y)
     assert loss.dim() == 0
     (0.7 * loss).backward()
-    assert abs(float(loss) - float(z[name + "_loss"])) < 1e-5 * max(1.0, abs(float(loss)))
+    assert abs(loss.item() - float(z[name + "_loss"])) < 1e-5 * max(1.0, abs(loss.item()))
     assert rel_err(n(x.grad), 0.7 * z[name + "_gx"]) < TOL_STAT and rel_err(n(y.grad), 0.7 * z[name + "_gy"]) < TOL_STAT
 
 
@@ -208,7 +208,7 @@ def test_mec_vs_oracle_batch64(dev):
     xt, yt = t(x, dev).requires_grad_(True), t(y, dev).requires_grad_(True)
     loss = consensus_loss.MinEntropyConsensusLoss(65, dev)(xt, yt)
     loss.backward()
-    assert abs(float(loss) - loss_o) < 1e-5 and rel_err(n(xt.grad), gx_o) < TOL_STAT and rel_err(n(yt.grad), gy_o) < TOL_STAT
+    assert abs(loss.item() - loss_o) < 1e-5 and rel_err(n(xt.grad), gx_o) < TOL_STAT and rel_err(n(yt.grad), gy_o) < TOL_STAT
 
 
 # --------------------------------------------------------------------------- fused domain triple
