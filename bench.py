@@ -44,6 +44,19 @@ LAMBDA_MEC = 0.1                                 # resnet50_dwt_mec_officehome.p
 NUM_CLASSES = 65
 
 
+def host_cores() -> int:
+    """Usable host cores: min(affinity mask, cgroup CPU quota).  The GPU boxes expose 128 logical
+    CPUs but cap the container at 16 by cgroup quota; oversubscribing the quota is ~10x slower."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -136,7 +149,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     per_domain = args.cpu_per_domain
     dev = torch.device("cpu")
@@ -181,7 +194,7 @@ def cpu_baseline(args):
         out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600).stdout.strip().splitlines()
         return json.loads(out[-1])["cpu_baseline"]
     except Exception as e:                                   # the GPU number must not die with the CPU leg
-        return {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        return {"value": None, "unit": "images/s", "cores": host_cores(), "kind": "port", "sample": f"failed: {e}"}
 
 
 def timed_loop(step_fn, steps, device, distributed):
@@ -251,7 +264,8 @@ def run_ours(args):
     with ClockSampler(local) as clocks:
         _native.profile_begin()
         ms = timed_loop(step_resident, args.steps, device, distributed)
-        prof = _native.profile_end()
+        prof_sites = _native.profile_end()
+    prof = _native.by_family(prof_sites)
     launches = (_native.launch_count() - n0) // args.steps
     for _ in range(2):
         step_e2e()
@@ -265,6 +279,13 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peaks()
+    if args.sites_out:
+        rows = [dict(zip(("kernel", "C", "HW", "GS", "D", "N"), k.split("|")), launches=v["launches"],
+                     us_per_launch=1e3 * v["ms"] / v["launches"], gbs=v["bytes"] / max(v["ms"], 1e-9) / 1e6,
+                     frac_of_peak=v["bytes"] / max(v["ms"], 1e-9) / 1e6 / peak, ms_per_step=v["ms"] / args.steps)
+                for k, v in sorted(prof_sites.items(), key=lambda kv: -kv[1]["ms"])]
+        os.makedirs(os.path.dirname(os.path.abspath(args.sites_out)), exist_ok=True)
+        json.dump(rows, open(args.sites_out, "w"), indent=1)
     fams = {k: dict(v, gbs=(v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None),
                     us_per_launch=(1e3 * v["ms"] / v["launches"] if v["launches"] else None),
                     share_of_step=v["ms"] / ms) for k, v in prof.items()}
@@ -314,7 +335,7 @@ def run_microbench(args, device, rank):
     with ClockSampler(device.index) as clocks:
         _native.profile_begin()
         ms = timed_loop(step, args.steps, device, False)
-        prof = _native.profile_end()
+        prof = _native.by_family(_native.profile_end())
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
@@ -346,6 +367,7 @@ def main():
     ap.add_argument("--site-mode", choices=["fused", "modules"], default="fused")
     ap.add_argument("--cpu-per-domain", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--sites-out", default="", help="write the per-site kernel table (JSON) here")
     ap.add_argument("--micro-n", type=int, default=256)
     ap.add_argument("--micro-gs", type=int, default=64)
     args = ap.parse_args()

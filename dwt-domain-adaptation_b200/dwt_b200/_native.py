@@ -62,10 +62,21 @@ def profile_begin():
 
 
 def profile_end():
-    """-> {kernel family: dict(launches, ms, bytes)}; waits for the recorded events."""
-    buf = (ProfileEntry * 32)()
-    k = lib().dwt_profile_end(ctypes.cast(buf, ctypes.c_void_p), 32)
+    """-> {"family|C|HW|GS|D|N": dict(launches, ms, bytes)}; waits for the recorded events."""
+    cap = 1024
+    buf = (ProfileEntry * cap)()
+    k = lib().dwt_profile_end(ctypes.cast(buf, ctypes.c_void_p), cap)
     return {buf[i].name.decode(): dict(launches=buf[i].launches, ms=buf[i].ms, bytes=buf[i].bytes) for i in range(k)}
+
+
+def by_family(prof):
+    """Collapse profile_end() output over geometries: {family: dict(launches, ms, bytes)}."""
+    out = {}
+    for name, v in prof.items():
+        f = out.setdefault(name.split("|")[0], dict(launches=0, ms=0.0, bytes=0.0))
+        for k in f:
+            f[k] += v[k]
+    return out
 
 
 def launch_count() -> int:

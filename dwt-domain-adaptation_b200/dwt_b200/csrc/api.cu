@@ -48,7 +48,7 @@ int sm_count() {
 std::atomic<int64_t> g_launches{0};
 std::mutex g_prof_mu;
 bool g_prof_on = false;
-struct ProfRec { const char* name; cudaEvent_t a, b; double bytes; };
+struct ProfRec { char name[48]; cudaEvent_t a, b; double bytes; };
 std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_event_pool;
 
@@ -62,7 +62,11 @@ cudaEvent_t take_event() {
 // RAII bracket around one kernel launch
 struct Launch {
   cudaStream_t st; ProfRec rec; bool on;
-  Launch(const char* name, double bytes, cudaStream_t s) : st(s), rec{name, nullptr, nullptr, bytes}, on(false) {
+  // name = "<kernel family>|C|HW|GS|D|N" so the bench can break time down by norm site
+  Launch(const char* family, const dwt::Geom* gm, double bytes, cudaStream_t s) : st(s), on(false) {
+    rec.a = rec.b = nullptr; rec.bytes = bytes;
+    if (gm) snprintf(rec.name, sizeof(rec.name), "%s|%d|%d|%d|%d|%d", family, gm->C, gm->HW, gm->GS, gm->D, gm->N);
+    else snprintf(rec.name, sizeof(rec.name), "%s", family);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (g_prof_on && g_prof.size() < (1u << 18)) {
@@ -201,17 +205,17 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
 
   const double E = 4.0 * (double)D * (double)N * (double)C * (double)HW;   // bytes of one activation tensor
   if (mode == DWT_MODE_TRAIN) {
-    Launch l(p.small ? "small_stats" : "tiled_stats", E, st);
+    Launch l(p.small ? "small_stats" : "tiled_stats", &p.gm, E, st);
     if (p.small) dwt::small_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
     else dwt::tiled_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
   } else {
-    Launch l("eval_prep", 0.0, st);
+    Launch l("eval_prep", &p.gm, 0.0, st);
     if (p.small) dwt::small_eval_prep(p.gm, fin, st);
     else dwt::tiled_eval_prep(p.gm, fin, st);
   }
   if (int rc = check_launch("whitening statistics kernel")) return rc;
   {
-    Launch l(p.small ? "small_apply" : "tiled_apply", 2 * E, st);
+    Launch l(p.small ? "small_apply" : "tiled_apply", &p.gm, 2 * E, st);
     if (p.small) dwt::small_apply(x, y, p.gm, p.vec, p.chunks_ew, epi, save_mean, save_w, gamma, beta, st);
     else dwt::tiled_apply(x, y, p.gm, p.vec, p.chunks_ew, save_mean, save_w, st);
   }
@@ -247,17 +251,17 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
   const bool need_reduce = (mode == DWT_MODE_TRAIN) || (fin.dgamma != nullptr);
   const double E = 4.0 * (double)D * (double)N * (double)C * (double)HW;
   if (need_reduce) {
-    Launch l(p.small ? "small_bwd_reduce" : "tiled_bwd_reduce", 2 * E, st);
+    Launch l(p.small ? "small_bwd_reduce" : "tiled_bwd_reduce", &p.gm, 2 * E, st);
     if (p.small) dwt::small_bwd_reduce(x, dout, p.gm, p.vec, fin, beta, w.partial, w.counters, st);
     else dwt::tiled_bwd_reduce(x, dout, p.gm, p.vec, fin, w.partial, w.counters, st);
   } else {
-    Launch l("bwd_prep", 0.0, st);
+    Launch l("bwd_prep", &p.gm, 0.0, st);
     if (p.small) dwt::small_bwd_prep(p.gm, fin, st);
     else dwt::tiled_bwd_prep(p.gm, fin, st);
   }
   if (int rc = check_launch("whitening backward reduction kernel")) return rc;
   {
-    Launch l(p.small ? "small_bwd_apply" : "tiled_bwd_apply", 3 * E, st);
+    Launch l(p.small ? "small_bwd_apply" : "tiled_bwd_apply", &p.gm, 3 * E, st);
     if (p.small) dwt::small_bwd_apply(x, dout, dx, p.gm, p.vec, p.chunks_ew, epi, w.coef, save_mean, save_w, gamma, beta, st);
     else dwt::tiled_bwd_apply(x, dout, dx, p.gm, p.vec, p.chunks_ew, w.coef, st);
   }
@@ -323,7 +327,7 @@ int dwt_mec_fwd_bwd(const float* x, const float* y, int64_t N, int64_t K, float*
   if (!x || !y || !loss || !gx || !gy) return fail(DWT_E_INVALID, "null pointer argument");
   if (N <= 0 || K <= 0 || N >= (1 << 24) || K >= (1 << 24)) return fail(DWT_E_INVALID, "bad logits shape [%lld,%lld]", (long long)N, (long long)K);
   {
-    Launch l("mec", 16.0 * (double)N * (double)K, (cudaStream_t)stream);
+    Launch l("mec", nullptr, 16.0 * (double)N * (double)K, (cudaStream_t)stream);
     dwt::mec_launch(x, y, (int)N, (int)K, loss, gx, gy, (cudaStream_t)stream);
   }
   return check_launch("MEC kernel");

@@ -165,7 +165,7 @@ def resnet_case():
     import resnet50_dwt_mec_officehome as script
     os.chdir(cwd)
     sd = synth_state_dict(seed=1)
-    x, labels = synth_batch(seed=2, per_domain=2, size=64)
+    x, labels = synth_batch(seed=2, per_domain=4, size=96)
     model = script.ResNet(script.Bottleneck, [3, 4, 6, 3], {k: v.clone() for k, v in sd.items()})
     model.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
     model.train()

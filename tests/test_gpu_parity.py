@@ -295,7 +295,8 @@ def test_microbench_shape_properties(dev):
     S = (1 - eps) * sigma + eps * torch.eye(gs, device=dev, dtype=torch.float64)
     W_ref = torch.linalg.inv(torch.linalg.cholesky(S))
     y_ref = (W_ref @ xc).reshape(C, N, H, H).transpose(0, 1)
-    assert rel_err(n(y), n(y_ref)) < TOL
+    assert ((y.detach().double() - y_ref).norm() / y_ref.norm()).item() < TOL
+    del y_ref, xc, xg, yg
     ident = (1 - eps) * cov_y + eps * (W_ref @ W_ref.transpose(1, 2))
     assert (ident - torch.eye(gs, device=dev, dtype=torch.float64)).abs().max() < 1e-3
     dy = torch.randn_like(y)
@@ -322,7 +323,7 @@ def test_resnet_site_fullsize_idempotence(dev):
         y2 = m(y)
     # cov(y) = (I - eps W W^T)/(1-eps); second pass sees S2 = I - eps W W^T + eps I, whose Cholesky inverse is
     # within O(eps * ||W W^T - I||) of I.  For this well-conditioned input (var 9): W W^T ~ I/9.
-    assert rel_err(n(y2[:4]), n(y[:4])) < 2e-3
+    assert ((y2 - y).double().norm() / y.double().norm()).item() < 2e-3
     assert y.mean(dim=(0, 2, 3)).abs().max() < 1e-4
 
 
@@ -337,7 +338,7 @@ def test_resnet_tiny_vs_reference_golden(site_mode, dev):
     from harness.synth import synth_batch, synth_state_dict
     z = np.load(os.path.join(HERE, "resnet_tiny.npz"))
     sd = {k: v.to(dev) for k, v in synth_state_dict(seed=1).items()}
-    x, labels = synth_batch(seed=2, per_domain=2, size=64)
+    x, labels = synth_batch(seed=2, per_domain=4, size=96)
     model = build_resnet50_dwt(sd, dwt_b200, site_mode=site_mode).to(dev).train()
     logits = model(x.to(dev))
     s, tt, a = torch.split(logits, logits.shape[0] // 3, dim=0)
@@ -345,7 +346,7 @@ def test_resnet_tiny_vs_reference_golden(site_mode, dev):
     mec = 0.1 * dwt_b200.MinEntropyConsensusLoss(65, dev)(tt, a)
     (cls + mec).backward()
     assert rel_err(n(logits), z["logits"]) < 5e-3          # 53 norm sites deep; per-layer bar is 1e-3
-    assert abs(float(cls) - float(z["cls_loss"])) < 5e-3 and abs(float(mec) - float(z["mec_loss"])) < 5e-3
+    assert abs(cls.item() - float(z["cls_loss"])) < 5e-3 and abs(mec.item() - float(z["mec_loss"])) < 5e-3
     params = dict(model.named_parameters())
     for k in [k[5:] for k in z.files if k.startswith("grad/")]:
         assert rel_err(n(params[k].grad), z["grad/" + k]) < 2e-2, k
