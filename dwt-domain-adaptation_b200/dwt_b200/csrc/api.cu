@@ -91,10 +91,25 @@ int ensure_tiled() {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Upper bound of CTAs cooperating on one (domain, group): enough CTAs to fill the machine
-// a few times over, split evenly over the D*G independent problems.
+// Launch shaping.  Every norm kernel is a single wave of long-lived CTAs: `target` CTAs in total
+// (a small multiple of the SM count, set by the kernel's register footprint), reached either by
+// splitting each (domain, group) problem over `nchunks` CTAs (few large problems) or by serving
+// `ppc` problems per CTA (thousands of small ones).
+enum KernelKind { K_STATS, K_APPLY, K_BWD_REDUCE, K_BWD_APPLY };
+
+int target_ctas(KernelKind k, int GS) {
+  const int sms = sm_count();
+  if (GS > 4) return 2 * sms;                              // tiled path: 2-3 CTAs/SM by shared memory
+  switch (k) {
+    case K_BWD_REDUCE: return (GS == 4 ? 2 : 4) * sms;     // ~98 registers/thread at GS=4
+    case K_BWD_APPLY: return (GS == 4 ? 3 : 4) * sms;
+    default: return 4 * sms;
+  }
+}
+
+// Largest split any kernel may use for one problem: sizes the partials area of the workspace.
 int chunk_cap(int GS, int G, int D) {
-  const int target = sm_count() * (GS <= 4 ? 8 : 2);
+  const int target = 4 * sm_count();
   int cap = (target + G * D - 1) / (G * D);
   return cap < 1 ? 1 : cap;
 }
@@ -140,21 +155,40 @@ Workspace carve(void* base, int64_t C, int GS, int D) {
 }
 
 struct Plan {
-  dwt::Geom gm;
-  int vec;        // 4 when rows can be read as float4
-  int chunks_ew;  // grid.x of the elementwise (apply) kernels
+  dwt::Geom gm;       // gm.nchunks / gm.ppc shaped for the REDUCTION kernel of this call
+  dwt::Geom gm_ew;    // same geometry shaped for the elementwise kernel of this call
+  int vec;            // 4 when rows can be read as float4
+  int chunks_ew;      // grid.x of the elementwise (apply) kernel
   bool small;
 };
 
-int make_plan(Plan& p, const void* a0, const void* a1, const void* a2, int64_t N, int64_t C, int64_t HW, int GS,
-              int D) {
+void shape(dwt::Geom& g, int64_t work_units, KernelKind kind, bool small, int* chunks) {
+  const int target = target_ctas(kind, g.GS);
+  const int problems = g.G * g.D;
+  g.ppc = 1;
+  if (small)
+    for (int p = 8; p > 1; p >>= 1)
+      if ((int64_t)(g.G + p - 1) / p * g.D * 5 >= (int64_t)target * 3) { g.ppc = p; break; }
+  int n = 1;
+  if (g.ppc == 1) {
+    n = (target + problems / 2) / problems;
+    const int cap = chunk_cap(g.GS, g.G, g.D);
+    if (n > cap) n = cap;
+    if (n > work_units) n = (int)work_units;
+    if (n < 1) n = 1;
+  }
+  *chunks = n;
+}
+
+int make_plan(Plan& p, KernelKind reduce_kind, KernelKind ew_kind, const void* a0, const void* a1, const void* a2,
+              int64_t N, int64_t C, int64_t HW, int GS, int D) {
   if (N <= 0 || C <= 0 || HW <= 0) return fail(DWT_E_INVALID, "empty tensor (N=%lld C=%lld HW=%lld)", (long long)N,
                                                (long long)C, (long long)HW);
   if (GS < 1 || GS > DWT_MAX_GROUP_SIZE) return fail(DWT_E_UNSUPPORTED, "group_size %d outside [1,%d]", GS,
                                                      DWT_MAX_GROUP_SIZE);
   if (C % GS != 0) return fail(DWT_E_INVALID, "channels %lld not divisible by group_size %d", (long long)C, GS);
   if (D < 1 || D > DWT_MAX_DOMAINS) return fail(DWT_E_INVALID, "n_domains %d outside [1,%d]", D, DWT_MAX_DOMAINS);
-  if (N * HW >= (int64_t)1 << 31 || C * HW >= (int64_t)1 << 31 || C / GS > 65535)
+  if (N * C * HW >= (int64_t)1 << 31 || C / GS > 65535)
     return fail(DWT_E_UNSUPPORTED, "shape too large for 32-bit item indexing");
   dwt::Geom& g = p.gm;
   g.N = (int)N; g.C = (int)C; g.HW = (int)HW; g.GS = GS; g.G = (int)(C / GS); g.D = D;
@@ -162,14 +196,14 @@ int make_plan(Plan& p, const void* a0, const void* a1, const void* a2, int64_t N
   const uintptr_t bits = (uintptr_t)a0 | (uintptr_t)a1 | (uintptr_t)a2;
   p.vec = (HW % 4 == 0 && bits % 16 == 0) ? 4 : 1;
   p.small = dwt::small_supports(GS);
-  const int cap = chunk_cap(GS, g.G, D);
-  int64_t work_units;   // CTA-iterations available per (domain, group)
-  if (p.small) work_units = (N * (HW / p.vec) + dwt::kThreads * 4 - 1) / (dwt::kThreads * 4);
+  int64_t work_units;   // CTA-sized pieces of work available per (domain, group)
+  if (p.small) work_units = (N * (HW / p.vec) + dwt::kThreads * 2 - 1) / (dwt::kThreads * 2);
   else work_units = (N * HW + 127) / 128;
   if (work_units < 1) work_units = 1;
-  g.nchunks = (int)(work_units < cap ? work_units : cap);
-  const int ew_cap = cap * 2;
-  p.chunks_ew = (int)(work_units < ew_cap ? work_units : ew_cap);
+  shape(g, work_units, reduce_kind, p.small, &g.nchunks);
+  p.gm_ew = g;
+  shape(p.gm_ew, work_units, ew_kind, p.small, &p.chunks_ew);
+  p.gm_ew.nchunks = g.nchunks;
   return DWT_OK;
 }
 
@@ -178,7 +212,7 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
                     float* const* rcov, const float* gamma, const float* beta, int epi, float* save_mean,
                     float* save_w, void* ws, size_t ws_bytes, cudaStream_t st) {
   Plan p;
-  if (int rc = make_plan(p, x, y, nullptr, N, C, HW, GS, D)) return rc;
+  if (int rc = make_plan(p, K_STATS, K_APPLY, x, y, nullptr, N, C, HW, GS, D)) return rc;
   if (!x || !y || !save_mean || !save_w || !ws) return fail(DWT_E_INVALID, "null pointer argument");
   if (mode != DWT_MODE_TRAIN && mode != DWT_MODE_EVAL) return fail(DWT_E_INVALID, "bad mode %d", mode);
   if ((epi & DWT_EPI_RELU) && !(epi & DWT_EPI_AFFINE)) return fail(DWT_E_INVALID, "RELU epilogue needs AFFINE");
@@ -216,8 +250,8 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
   if (int rc = check_launch("whitening statistics kernel")) return rc;
   {
     Launch l(p.small ? "small_apply" : "tiled_apply", &p.gm, 2 * E, st);
-    if (p.small) dwt::small_apply(x, y, p.gm, p.vec, p.chunks_ew, epi, save_mean, save_w, gamma, beta, st);
-    else dwt::tiled_apply(x, y, p.gm, p.vec, p.chunks_ew, save_mean, save_w, st);
+    if (p.small) dwt::small_apply(x, y, p.gm_ew, p.vec, p.chunks_ew, epi, save_mean, save_w, gamma, beta, st);
+    else dwt::tiled_apply(x, y, p.gm_ew, p.vec, p.chunks_ew, save_mean, save_w, st);
   }
   return check_launch("whitening apply kernel");
 }
@@ -227,7 +261,7 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
                     const float* beta, int epi, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
                     cudaStream_t st) {
   Plan p;
-  if (int rc = make_plan(p, x, dout, dx, N, C, HW, GS, D)) return rc;
+  if (int rc = make_plan(p, K_BWD_REDUCE, K_BWD_APPLY, x, dout, dx, N, C, HW, GS, D)) return rc;
   if (!x || !dout || !dx || !save_mean || !save_w || !ws) return fail(DWT_E_INVALID, "null pointer argument");
   if (mode != DWT_MODE_TRAIN && mode != DWT_MODE_EVAL) return fail(DWT_E_INVALID, "bad mode %d", mode);
   if ((epi & DWT_EPI_RELU) && !(epi & DWT_EPI_AFFINE)) return fail(DWT_E_INVALID, "RELU epilogue needs AFFINE");
@@ -262,8 +296,8 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
   if (int rc = check_launch("whitening backward reduction kernel")) return rc;
   {
     Launch l(p.small ? "small_bwd_apply" : "tiled_bwd_apply", &p.gm, 3 * E, st);
-    if (p.small) dwt::small_bwd_apply(x, dout, dx, p.gm, p.vec, p.chunks_ew, epi, w.coef, save_mean, save_w, gamma, beta, st);
-    else dwt::tiled_bwd_apply(x, dout, dx, p.gm, p.vec, p.chunks_ew, w.coef, st);
+    if (p.small) dwt::small_bwd_apply(x, dout, dx, p.gm_ew, p.vec, p.chunks_ew, epi, w.coef, save_mean, save_w, gamma, beta, st);
+    else dwt::tiled_bwd_apply(x, dout, dx, p.gm_ew, p.vec, p.chunks_ew, w.coef, st);
   }
   return check_launch("whitening backward apply kernel");
 }

@@ -28,6 +28,7 @@ struct Geom {
   int G;        // C / GS
   int D;        // domains
   int nchunks;  // CTAs cooperating on one (domain, group)
+  int ppc;      // (domain, group) problems served by one CTA (register-resident path; 1, 2, 4 or 8)
   float M;      // N * HW as float
 };
 
