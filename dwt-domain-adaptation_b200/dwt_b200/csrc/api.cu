@@ -97,19 +97,17 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // `ppc` problems per CTA (thousands of small ones).
 enum KernelKind { K_STATS, K_APPLY, K_BWD_REDUCE, K_BWD_APPLY };
 
-int target_ctas(KernelKind k, int GS) {
-  const int sms = sm_count();
-  if (GS > 4) return 2 * sms;                              // tiled path: 2-3 CTAs/SM by shared memory
-  switch (k) {
-    case K_BWD_REDUCE: return (GS == 4 ? 2 : 4) * sms;     // ~98 registers/thread at GS=4
-    case K_BWD_APPLY: return (GS == 4 ? 3 : 4) * sms;
-    default: return 4 * sms;
-  }
+// Resident CTAs per SM of each kernel (its __launch_bounds__ minimum); reductions launch at most
+// one full wave of equal-work CTAs (no tail), elementwise kernels many short CTAs (>= 4 waves).
+int slots_per_sm(KernelKind k, int GS) {
+  if (GS > 4) return 2;                                    // tiled path: limited by shared memory
+  return ((k == K_STATS || k == K_APPLY) && GS < 4) ? 4 : 3;
 }
 
 // Largest split any kernel may use for one problem: sizes the partials area of the workspace.
 int chunk_cap(int GS, int G, int D) {
-  const int target = 4 * sm_count();
+  (void)GS;
+  const int target = 16 * sm_count();
   int cap = (target + G * D - 1) / (G * D);
   return cap < 1 ? 1 : cap;
 }
@@ -163,15 +161,17 @@ struct Plan {
 };
 
 void shape(dwt::Geom& g, int64_t work_units, KernelKind kind, bool small, int* chunks) {
-  const int target = target_ctas(kind, g.GS);
-  const int problems = g.G * g.D;
+  const bool reduce = (kind == K_STATS || kind == K_BWD_REDUCE);
+  const int slots = slots_per_sm(kind, g.GS) * sm_count();
+  const int target = reduce ? slots : 4 * slots;
   g.ppc = 1;
-  if (small)
-    for (int p = 8; p > 1; p >>= 1)
-      if ((int64_t)(g.G + p - 1) / p * g.D * 5 >= (int64_t)target * 3) { g.ppc = p; break; }
+  if (small) {
+    // smallest team split that fits the problems of this site into `target` CTAs
+    while (g.ppc < 8 && (int64_t)((g.G + g.ppc - 1) / g.ppc) * g.D > target) g.ppc <<= 1;
+  }
   int n = 1;
   if (g.ppc == 1) {
-    n = (target + problems / 2) / problems;
+    n = target / (g.G * g.D);                              // floor: never spill into a second wave
     const int cap = chunk_cap(g.GS, g.G, g.D);
     if (n > cap) n = cap;
     if (n > work_units) n = (int)work_units;

@@ -340,7 +340,7 @@ __device__ __forceinline__ bool team_reduce(const Geom& gm, const Team& tm, int 
 // stats
 // ------------------------------------------------------------------------------------------
 template <int GS, int VEC>
-__global__ void __launch_bounds__(kThreads) small_stats_kernel(const float* __restrict__ x, const Geom gm,
+__global__ void __launch_bounds__(kThreads, (GS * VEC >= 16) ? 3 : 4) small_stats_kernel(const float* __restrict__ x, const Geom gm,
                                                                 const FwdFin fin, float* __restrict__ partial,
                                                                 int* counters) {
   constexpr int NM = GS * (GS + 1) / 2, NACC = GS + NM, UNROLL = Unroll<GS, VEC>::stats;
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(kThreads) small_eval_prep_kernel(const Geom gm
 // apply
 // ------------------------------------------------------------------------------------------
 template <int GS, int VEC, int EPI>
-__global__ void __launch_bounds__(kThreads) small_apply_kernel(const float* __restrict__ x, float* __restrict__ y,
+__global__ void __launch_bounds__(kThreads, (GS * VEC >= 16) ? 3 : 4) small_apply_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                 const Geom gm, const float* __restrict__ save_mean,
                                                                 const float* __restrict__ save_w,
                                                                 const float* __restrict__ gamma,
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(kThreads) small_apply_kernel(const float* __re
 // backward reduce
 // ------------------------------------------------------------------------------------------
 template <int GS, int VEC, int EPI>
-__global__ void __launch_bounds__(kThreads) small_bwd_reduce_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(kThreads, 3) small_bwd_reduce_kernel(const float* __restrict__ x,
                                                                      const float* __restrict__ dout, const Geom gm,
                                                                      const BwdFin fin, const float* __restrict__ beta,
                                                                      float* __restrict__ partial, int* counters) {
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(kThreads) small_bwd_prep_kernel(const Geom gm,
 // backward apply
 // ------------------------------------------------------------------------------------------
 template <int GS, int VEC, int EPI>
-__global__ void __launch_bounds__(kThreads) small_bwd_apply_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(kThreads, 3) small_bwd_apply_kernel(const float* __restrict__ x,
                                                                     const float* __restrict__ dout,
                                                                     float* __restrict__ dx, const Geom gm,
                                                                     const float* __restrict__ coef,
