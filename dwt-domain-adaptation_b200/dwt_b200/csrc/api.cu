@@ -236,6 +236,15 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
   fin.save_mean = save_mean; fin.save_w = save_w; fin.save_cov = w.save_cov;
   for (int d = 0; d < D; ++d) { fin.rmean[d] = need_running ? rmean[d] : nullptr; fin.rcov[d] = need_running ? rcov[d] : nullptr; }
   fin.dom_counter = w.dom_counter; fin.status = w.status;
+  if (need_running && D > 1) {
+    bool all_same = true, all_distinct = true;
+    for (int d = 1; d < D; ++d) {
+      if (rmean[d] != rmean[0] || rcov[d] != rcov[0]) all_same = false;
+      for (int e = 0; e < d; ++e)
+        if (rmean[d] == rmean[e] || rcov[d] == rcov[e]) all_distinct = false;
+    }
+    fin.aliased = all_same ? 1 : (all_distinct ? 0 : -1);
+  }
 
   const double E = 4.0 * (double)D * (double)N * (double)C * (double)HW;   // bytes of one activation tensor
   if (mode == DWT_MODE_TRAIN) {

@@ -37,6 +37,8 @@ struct FwdFin {
   float momentum;        // EMA weight of the new statistic
   float unbias;          // factor on the covariance going into the EMA (M/(M-1) for batch norm)
   int update_running;
+  int aliased;           // 1: every domain updates the SAME running buffers (ordered EMA collapses to a closed form)
+                         // 0: all distinct (independent updates); -1: mixed (ordered, domain by domain)
   float* save_mean;      // [D][C]
   float* save_w;         // [D][G][GS*GS]
   float* save_cov;       // [D][G][GS*GS] workspace: batch covariance, read back for the ordered EMA

@@ -171,30 +171,58 @@ __device__ __forceinline__ void factor_thread(const Geom& gm, const FwdFin& f, i
 // EMA of the running buffers by one thread, domains in order.  With several
 // domains the thread that finalizes the LAST domain of group g applies all D updates.
 template <int GS>
-__device__ __forceinline__ void ema_thread(const Geom& gm, const FwdFin& f, int g) {
+__device__ __forceinline__ void ema_thread(const Geom& gm, const FwdFin& f, int d_self, int g,
+                                           const float (&mean)[GS], const float (&cov)[GS][GS]) {
   if (!f.update_running) return;
-  if (gm.D > 1) {
-    __threadfence();
-    const int t = atomicAdd(f.dom_counter + g, 1);
-    if (t != gm.D - 1) return;
-    atomicExch(f.dom_counter + g, 0);
-    __threadfence();
-  }
   const float m = f.momentum, k = 1.f - f.momentum;
-  for (int d = 0; d < gm.D; ++d) {
-    const float* cov = f.save_cov + ((size_t)d * gm.G + g) * GS * GS;
+  if (gm.D == 1 || f.aliased == 0) {
+    // this domain owns its buffers: update them directly from registers, no cross-CTA traffic
+    float* rc = f.rcov[d_self] + (size_t)g * GS * GS;
+    float* rm = f.rmean[d_self] + g * GS;
+#pragma unroll
+    for (int i = 0; i < GS; ++i) {
+      rm[i] = m * mean[i] + k * rm[i];
+#pragma unroll
+      for (int j = 0; j < GS; ++j) rc[i * GS + j] = m * (cov[i][j] * f.unbias) + k * rc[i * GS + j];
+    }
+    return;
+  }
+  // shared buffers: the thread that finalizes the LAST domain of group g applies all D updates
+  __threadfence();
+  const int t = atomicAdd(f.dom_counter + g, 1);
+  if (t != gm.D - 1) return;
+  atomicExch(f.dom_counter + g, 0);
+  __threadfence();
+  if (f.aliased == 1) {
+    // r' = k^D r + m * sum_d k^(D-1-d) s_d  ==  D sequential updates of one buffer
+    float* rc = f.rcov[0] + (size_t)g * GS * GS;
+    float* rm = f.rmean[0] + g * GS;
+    float c[GS * GS], u[GS];
+#pragma unroll
+    for (int e = 0; e < GS * GS; ++e) c[e] = rc[e];
+#pragma unroll
+    for (int e = 0; e < GS; ++e) u[e] = rm[e];
+    for (int d = 0; d < gm.D; ++d) {
+      const float* cv = f.save_cov + ((size_t)d * gm.G + g) * GS * GS;
+      const float* mu = f.save_mean + (size_t)d * gm.C + g * GS;
+#pragma unroll
+      for (int e = 0; e < GS * GS; ++e) c[e] = m * (__ldcg(cv + e) * f.unbias) + k * c[e];
+#pragma unroll
+      for (int e = 0; e < GS; ++e) u[e] = m * __ldcg(mu + e) + k * u[e];
+    }
+#pragma unroll
+    for (int e = 0; e < GS * GS; ++e) rc[e] = c[e];
+#pragma unroll
+    for (int e = 0; e < GS; ++e) rm[e] = u[e];
+    return;
+  }
+  for (int d = 0; d < gm.D; ++d) {       // mixed aliasing: plain ordered read-modify-write
+    const float* cv = f.save_cov + ((size_t)d * gm.G + g) * GS * GS;
     const float* mu = f.save_mean + (size_t)d * gm.C + g * GS;
     float* rc = f.rcov[d] + (size_t)g * GS * GS;
     float* rm = f.rmean[d] + g * GS;
-    float c[GS * GS], u[GS];
-#pragma unroll
-    for (int e = 0; e < GS * GS; ++e) c[e] = __ldcg(cov + e);
-#pragma unroll
-    for (int e = 0; e < GS; ++e) u[e] = __ldcg(mu + e);
-#pragma unroll
-    for (int e = 0; e < GS * GS; ++e) rc[e] = m * (c[e] * f.unbias) + k * rc[e];
-#pragma unroll
-    for (int e = 0; e < GS; ++e) rm[e] = m * u[e] + k * rm[e];
+    for (int e = 0; e < GS * GS; ++e) rc[e] = m * (__ldcg(cv + e) * f.unbias) + k * rc[e];
+    for (int e = 0; e < GS; ++e) rm[e] = m * __ldcg(mu + e) + k * rm[e];
   }
 }
 
@@ -427,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, (GS * VEC >= 16) ? 3 : 4) small_stat
       cov[i][j] = cij; cov[j][i] = cij;
     }
   factor_thread<GS>(gm, fin, d, tm.g, mean, cov, true);
-  ema_thread<GS>(gm, fin, tm.g);
+  ema_thread<GS>(gm, fin, d, tm.g, mean, cov);
 }
 
 // Eval mode: W and mean straight from the running buffers (whitening.py:42-43,50-53).

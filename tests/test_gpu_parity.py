@@ -348,11 +348,49 @@ def test_resnet_tiny_vs_reference_golden(site_mode, dev):
     assert rel_err(n(logits), z["logits"]) < 5e-3          # 53 norm sites deep; per-layer bar is 1e-3
     assert abs(cls.item() - float(z["cls_loss"])) < 5e-3 and abs(mec.item() - float(z["mec_loss"])) < 5e-3
     params = dict(model.named_parameters())
+    # Deep-gradient yardstick: the same model built from stock ATen ops (the CPU port of the reference
+    # layers, run on this GPU) differs from the CPU fp32 golden by cuDNN-vs-MKLDNN rounding amplified
+    # through 53 batch-statistics layers.  Our layers may not be worse than 2x that (floor 2e-2).
+    import oracle.torch_port as port
+    ref = build_resnet50_dwt({k: v.clone() for k, v in synth_state_dict(seed=1).items()}, port, site_mode="modules").to(dev).train()
+    rl = ref(x.to(dev))
+    rs, rt, ra = torch.split(rl, rl.shape[0] // 3, dim=0)
+    (Fn.nll_loss(Fn.log_softmax(rs, dim=1), labels.to(dev)) + 0.1 * port.MinEntropyConsensusLoss(65, dev)(rt, ra)).backward()
+    rparams = dict(ref.named_parameters())
     for k in [k[5:] for k in z.files if k.startswith("grad/")]:
-        assert rel_err(n(params[k].grad), z["grad/" + k]) < 2e-2, k
+        yard = rel_err(n(rparams[k].grad), z["grad/" + k])
+        assert rel_err(n(params[k].grad), z["grad/" + k]) < max(2e-2, 2 * yard), (k, yard)
     bufs = model.state_dict()
     for k in [k[4:] for k in z.files if k.startswith("buf/")]:
         assert rel_err(n(bufs[k]), z["buf/" + k]) < 1e-3, k
     model.eval()
     with torch.no_grad():
         assert rel_err(n(model(x.to(dev))), z["logits_eval"]) < 5e-3
+
+
+@pytest.mark.parametrize("layout", ["distinct", "mixed"])
+def test_fused_triple_buffer_aliasing_classes(layout, dev):
+    """The fused site must give each domain's running buffers exactly what three sequential module
+    calls give them, whether the three modules share one buffer (tested above), own three buffers,
+    or two of them share (source alone, target+aug shared)."""
+    import whitening
+    from dwt_b200 import DomainTripleNorm
+    rng = np.random.default_rng(21)
+    c, gs, nper, hw = 32, 4, 4, 12
+    x = np.concatenate([_correlated(rng, nper, c, hw, hw, offset=o) for o in (0.5, -1.0, 2.0)])
+    rm0 = 0.1 * rng.standard_normal(c)
+    a = rng.standard_normal((c // gs, gs, gs))
+    rv0 = a @ a.transpose(0, 2, 1) / gs + 0.5 * np.eye(gs)
+    owner = {"distinct": [0, 1, 2], "mixed": [0, 1, 1]}[layout]
+    bufs = {o: [rm0.copy(), rv0.copy()] for o in set(owner)}
+    for d in range(3):                                     # oracle: sequential calls
+        _, _, _, nrm, nrv, _ = O.whiten_forward(x[d * nper:(d + 1) * nper], gs, running_mean=bufs[owner[d]][0],
+                                                running_cov=bufs[owner[d]][1])
+        bufs[owner[d]] = [nrm, nrv]
+    tb = {o: (t(rm0.reshape(1, c, 1, 1), dev), t(rv0, dev)) for o in set(owner)}
+    mods = [whitening.WTransform2d(c, gs, running_m=tb[o][0], running_var=tb[o][1]).train() for o in owner]
+    g_t, b_t = torch.ones(c, 1, 1, device=dev), torch.zeros(c, 1, 1, device=dev)
+    with torch.no_grad():
+        DomainTripleNorm("whiten", c, gs)(t(x, dev), mods, g_t, b_t, relu=False)
+    for o in set(owner):
+        assert rel_err(n(tb[o][0]).reshape(-1), bufs[o][0]) < TOL_STAT and rel_err(n(tb[o][1]), bufs[o][1]) < TOL_STAT
