@@ -89,6 +89,22 @@ int ensure_tiled() {
   return g_tiled_rc;
 }
 
+std::once_flag g_tc_once;
+int g_tc_rc = 0;
+int ensure_tc() {
+  std::call_once(g_tc_once, [] { g_tc_rc = dwt::tc_init(); });
+  return g_tc_rc;
+}
+
+// CTAs per (domain, super-block) of the tensor-core contraction: one full wave of 2 CTAs per SM
+int tc_chunks(const dwt::Geom& g) {
+  const int problems = dwt::tc_superblocks(g) * g.D;
+  int n = 2 * sm_count() / problems;
+  const int64_t tiles = (int64_t)g.N * ((g.HW + 31) / 32);
+  if (n > tiles) n = (int)tiles;
+  return n < 1 ? 1 : n;
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Launch shaping.  Every norm kernel is a single wave of long-lived CTAs: `target` CTAs in total
@@ -144,7 +160,12 @@ Workspace carve(void* base, int64_t C, int GS, int D) {
   w.counters = reinterpret_cast<int*>(b + kOffCounters);
   w.dom_counter = reinterpret_cast<int*>(b + kOffDom1);
   w.dom_counter2 = reinterpret_cast<int*>(b + kOffDom2);
-  w.partial = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * cap * (GS * GS + GS)));
+  size_t partial_floats = (size_t)D * G * cap * (GS * GS + GS);
+  if (GS >= 8 && 64 % GS == 0) {                           // tensor-core contraction: per super-block partials
+    const size_t tc = ((size_t)2 * sm_count() + (size_t)((C + 63) / 64) * D) * (64 * 64 + 64);
+    if (tc > partial_floats) partial_floats = tc;
+  }
+  w.partial = reinterpret_cast<float*>(b + take(sizeof(float) * partial_floats));
   w.save_cov = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * GS * GS));
   w.coef = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * dwt::coef_stride(GS)));
   w.dgb_part = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * 2 * C));
@@ -247,10 +268,14 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
   }
 
   const double E = 4.0 * (double)D * (double)N * (double)C * (double)HW;   // bytes of one activation tensor
+  const bool tc = !p.small && dwt::tc_supports(p.gm, p.vec) && ensure_tc() == 0;
   if (mode == DWT_MODE_TRAIN) {
-    Launch l(p.small ? "small_stats" : "tiled_stats", &p.gm, E, st);
+    Launch l(p.small ? "small_stats" : (tc ? "tc_stats" : "tiled_stats"), &p.gm, E, st);
     if (p.small) dwt::small_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
-    else dwt::tiled_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
+    else if (tc) {
+      if (dwt::tc_stats(x, p.gm, tc_chunks(p.gm), fin, w.partial, w.counters, st) != 0)
+        return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed");
+    } else dwt::tiled_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
   } else {
     Launch l("eval_prep", &p.gm, 0.0, st);
     if (p.small) dwt::small_eval_prep(p.gm, fin, st);
@@ -293,10 +318,14 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
 
   const bool need_reduce = (mode == DWT_MODE_TRAIN) || (fin.dgamma != nullptr);
   const double E = 4.0 * (double)D * (double)N * (double)C * (double)HW;
+  const bool tc = !p.small && dwt::tc_supports(p.gm, p.vec) && ensure_tc() == 0;
   if (need_reduce) {
-    Launch l(p.small ? "small_bwd_reduce" : "tiled_bwd_reduce", &p.gm, 2 * E, st);
+    Launch l(p.small ? "small_bwd_reduce" : (tc ? "tc_bwd_reduce" : "tiled_bwd_reduce"), &p.gm, 2 * E, st);
     if (p.small) dwt::small_bwd_reduce(x, dout, p.gm, p.vec, fin, beta, w.partial, w.counters, st);
-    else dwt::tiled_bwd_reduce(x, dout, p.gm, p.vec, fin, w.partial, w.counters, st);
+    else if (tc) {
+      if (dwt::tc_bwd_reduce(x, dout, p.gm, tc_chunks(p.gm), fin, w.partial, w.counters, st) != 0)
+        return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed");
+    } else dwt::tiled_bwd_reduce(x, dout, p.gm, p.vec, fin, w.partial, w.counters, st);
   } else {
     Launch l("bwd_prep", &p.gm, 0.0, st);
     if (p.small) dwt::small_bwd_prep(p.gm, fin, st);

@@ -32,6 +32,15 @@ void tiled_bwd_prep(const Geom& gm, const BwdFin& fin, cudaStream_t st);
 void tiled_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int vec, int chunks,
                      const float* coef, cudaStream_t st);
 
+// TMA + tcgen05 contraction path, group sizes 8..64 tiling a 64-channel super-block  (norm_tc.cu)
+int tc_init();      // driver entry point for cuTensorMapEncodeTiled + shared-memory opt-in; 0 on success
+bool tc_supports(const Geom& gm, int vec);
+int tc_superblocks(const Geom& gm);
+int tc_stats(const float* x, const Geom& gm, int nchunks, const FwdFin& fin, float* partial, int* counters,
+             cudaStream_t st);
+int tc_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nchunks, const BwdFin& fin, float* partial,
+                  int* counters, cudaStream_t st);
+
 // MEC loss (mec.cu)
 void mec_launch(const float* x, const float* y, int N, int K, float* loss, float* gx, float* gy, cudaStream_t st);
 

@@ -1,0 +1,421 @@
+// Tensor-core path for the two CONTRACTIONS over the flattened N*H*W axis when groups are large
+// (group size 8..64, i.e. BASELINE.json config 2: C=256, group_size=64):
+//
+//   stats       G = sum_m (x-K)(x-K)^T        per 64-channel super-block (gs x gs diagonal blocks kept)
+//   bwd_reduce  R = sum_m dy (x-mean)^T
+//
+// 2*gs flop per 4 bytes read puts these above the FP32-core ridge but far below the TF32
+// tensor ridge: on tcgen05 they are HBM-bound.  Structure of one CTA
+// (192 threads, persistent over a contiguous range of [64 channels x 32 pixels] tiles):
+//
+//   warp 0      TMA producer: cp.async.bulk.tensor.3d (box 32 px x 64 ch x 1 image, SWIZZLE_128B)
+//               into an 8-stage shared-memory ring, mbarrier complete_tx.
+//   warps 2-5   transform: in place, tile <- RN_tf32(tile - shift[channel]) (zero outside the
+//               tensor), row sums in registers, fence.proxy.async, arrive on the stage's "ready" barrier.
+//               Round-to-NEAREST operands make the TF32 product errors zero-mean, so they average
+//               out over the M ~ 1e5..1e6 samples instead of biasing the covariance (truncation would).
+//   warp 1      MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::tf32, M=64 N=64 K=8,
+//               both operands K-major straight from the swizzled tile (NCHW rows ARE K-major: the
+//               reference's transposing copy, whitening.py:46, disappears), fp32 accumulator in TMEM;
+//               tcgen05.commit releases the stage back to the producer.
+//   epilogue    tcgen05.ld the 64x64 accumulator (M=64 layout: row r -> lane 32*(r/16) + r%16),
+//               per-CTA partial -> global, last-arriving CTA of the super-block reduces the partials
+//               in fixed order and runs the block-cooperative Cholesky / inverse / EMA (forward) or
+//               the coefficient algebra (backward) of dwt_common.cuh.
+//
+// Reference: utils/whitening.py:46-47 (/root/reference) and its autograd transpose.
+#include <cuda.h>
+
+#include "dwt_common.cuh"
+#include "norm_launch.h"
+
+namespace dwt {
+namespace {
+
+constexpr int kTcThreads = 192;
+constexpr int kTilePx = 32, kTileCh = 64;
+constexpr int kTileBytes = kTileCh * kTilePx * 4;       // 8192
+constexpr int kStagesStats = 8, kStagesBwd = 4;
+constexpr int kTmemCols = 64;
+constexpr uint32_t kSpinLimit = 1u << 27;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > kSpinLimit) __trap();          // a protocol bug must fail, not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {     // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(kTmemCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {   // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kTmemCols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread L gets TMEM lane base+L)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address
+// >> 4, LBO = 1 (unused with swizzle), SBO = 1024 B between 8-row groups, version 1, layout type 2.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M x N.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------------------------------
+// shared memory carve-up
+// ------------------------------------------------------------------------------------------
+struct TcBarriers {
+  uint64_t full[kStagesStats];
+  uint64_t ready[kStagesStats];
+  uint64_t empty[kStagesStats];
+  uint64_t accum;
+  uint32_t tmem_slot;
+  int flag;
+};
+
+// Tile range of this CTA inside its (domain, super-block) problem.
+struct TileRange {
+  int begin, end, PB;     // tiles [begin, end), pixel blocks per image
+  __device__ TileRange(const Geom& gm) {
+    PB = (gm.HW + kTilePx - 1) / kTilePx;
+    const long long T = (long long)gm.N * PB;
+    begin = (int)(T * blockIdx.x / gridDim.x);
+    end = (int)(T * (blockIdx.x + 1) / gridDim.x);
+  }
+};
+
+// In-place transform of one landed tile by the 128 transform threads:
+//   v <- RN_tf32(v - shift[row]) inside the tensor, 0 outside; returns per-thread row sums of (v - shift).
+// Chunk q = tt + 128*i (16-byte units): row = q >> 3, physical chunk jp = q & 7, logical chunk = jp ^ (row & 7).
+__device__ __forceinline__ void transform_tile(float* tile, int tt, const float (&shift)[4], int px0, int HW, int ch0,
+                                               int C, float (&rowsum)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = tt + 128 * i, row = q >> 3, jp = q & 7, j = jp ^ (row & 7);
+    float4* p = reinterpret_cast<float4*>(tile) + q;
+    float4 v = *p;
+    const int px = px0 + 4 * j;
+    const bool rowok = (ch0 + row) < C;
+    float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool ok = rowok && (px + k) < HW;
+      const float s = ok ? e[k] - shift[i] : 0.f;
+      rowsum[i] += s;
+      e[k] = round_tf32(s);
+    }
+    *p = make_float4(e[0], e[1], e[2], e[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// the contraction kernel.  TWO = false: G = sum xs xs^T (stats).  TWO = true: R = sum dy xc^T.
+// ------------------------------------------------------------------------------------------
+template <bool TWO>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
+                   const float* __restrict__ x, const Geom gm, const FwdFin ffin, const BwdFin bfin,
+                   float* __restrict__ partial, int* counters) {
+  constexpr int STAGES = TWO ? kStagesBwd : kStagesStats;
+  constexpr int NT = TWO ? 2 : 1;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ TcBarriers bars;
+  __shared__ float sShift[kTileCh];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int sb = blockIdx.y, d = blockIdx.z, ch0 = sb * kTileCh;
+  const TileRange tr(gm);
+  const int ntiles = tr.end - tr.begin;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.ready[s], 4); mbar_init(&bars.empty[s], 1); }
+    mbar_init(&bars.accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&bars.tmem_slot);
+  // shift per channel: pilot mean (stats) or the saved batch mean (backward)
+  if (tid >= 64 && tid < 128) {
+    const int r = tid - 64, c = ch0 + r;
+    float sh = 0.f;
+    if (c < gm.C) {
+      if (TWO) sh = bfin.save_mean[(size_t)d * gm.C + c];
+      else {
+        const int np = gm.HW < 32 ? gm.HW : 32, p0 = ((gm.HW - np) / 2) & ~3;
+        const float* px = x + ((size_t)d * gm.N * gm.C + c) * gm.HW + p0;
+        float a = 0.f;
+        for (int k = 0; k < np; ++k) a += __ldg(px + k);
+        sh = a / (float)np;
+      }
+    }
+    sShift[r] = sh;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = bars.tmem_slot;
+
+  float rowsum[4] = {0.f, 0.f, 0.f, 0.f};
+  const int tt = tid - 64;                       // transform thread index (warps 2..5)
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int it = 0; it < ntiles; ++it) {
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(&bars.empty[s], ph ^ 1);
+        const int t = tr.begin + it, n = t / tr.PB, pb = t - n * tr.PB;
+        uint8_t* dst = smem + (size_t)s * NT * kTileBytes;
+        mbar_arrive_expect_tx(&bars.full[s], NT * kTileBytes);
+        tma_load_3d(dst, &map_x, pb * kTilePx, ch0, d * gm.N + n, &bars.full[s]);
+        if (TWO) tma_load_3d(dst + kTileBytes, &map_g, pb * kTilePx, ch0, d * gm.N + n, &bars.full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_tf32(64, 64);
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % STAGES, ph = (it / STAGES) & 1;
+      mbar_wait(&bars.ready[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t xaddr = smem_u32(smem + (size_t)s * NT * kTileBytes);
+        const uint64_t xdesc = make_kmajor_sw128_desc(xaddr);
+        const uint64_t adesc = TWO ? make_kmajor_sw128_desc(xaddr + kTileBytes) : xdesc;   // A = dy tile (rows i)
+#pragma unroll
+        for (int k = 0; k < kTilePx / 8; ++k)
+          umma_tf32(tmem_d, adesc + 2 * k, xdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&bars.empty[s]);
+        if (it == ntiles - 1) umma_commit(&bars.accum);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== transform warps =====
+    float shift[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) shift[i] = sShift[(tt + 128 * i) >> 3];
+    const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+    float dummy[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % STAGES, ph = (it / STAGES) & 1;
+      mbar_wait(&bars.full[s], ph);
+      const int t = tr.begin + it, n = t / tr.PB, pb = t - n * tr.PB;
+      float* tile = reinterpret_cast<float*>(smem + (size_t)s * NT * kTileBytes);
+      if (TWO) {
+        transform_tile(tile, tt, shift, pb * kTilePx, gm.HW, ch0, gm.C, dummy);                     // xc
+        transform_tile(tile + kTileBytes / 4, tt, zero, pb * kTilePx, gm.HW, ch0, gm.C, rowsum);    // dy, sums
+      } else {
+        transform_tile(tile, tt, shift, pb * kTilePx, gm.HW, ch0, gm.C, rowsum);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.ready[s]);
+    }
+  }
+
+  // ===== epilogue: accumulator + row sums -> this CTA's partial row =====
+  const int nacc = kTileCh * kTileCh + kTileCh;
+  float* prow = partial + (((size_t)d * gridDim.y + sb) * gridDim.x + blockIdx.x) * nacc;
+  if (warp >= 2) {
+    if (ntiles > 0) {
+      mbar_wait(&bars.accum, 0);
+      tc_fence_after();
+      const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
+      float v[32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + half * 32, v);
+        if (lane < 16) {                           // M=64 accumulator: row = 16*quad + lane
+          float* dst = prow + (quad * 16 + lane) * kTileCh + half * 32;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            *reinterpret_cast<float4*>(dst + 4 * c4) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        }
+      }
+      tc_fence_before();
+    } else {
+      for (int e = tt; e < kTileCh * kTileCh; e += 128) prow[e] = 0.f;
+    }
+    // row sums: the 8 lanes that share a row are consecutive
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float s = rowsum[i];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if ((tt & 7) == 0) prow[kTileCh * kTileCh + ((tt + 128 * i) >> 3)] = s;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d); }
+
+  if (!arrive_is_last(counters + d * gridDim.y + sb, gridDim.x, &bars.flag)) return;
+
+  // ===== last CTA of the super-block: fixed-order reduction + finalize of its groups =====
+  float* sAcc = reinterpret_cast<float*>(smem);                       // [64*64 + 64]
+  float* scratch = sAcc + nacc;
+  __syncthreads();
+  reduce_partials(partial + ((size_t)d * gridDim.y + sb) * gridDim.x * nacc, gridDim.x, nacc, sAcc);
+  __syncthreads();
+  const int GS = gm.GS, LD = GS + 1, nb = kTileCh / GS;
+  const float invM = 1.f / gm.M;
+  for (int b = 0; b < nb; ++b) {
+    const int g = sb * nb + b, o = b * GS;
+    if (g >= gm.G) break;
+    if constexpr (!TWO) {
+      float* sMean = scratch;
+      float* sCov = sMean + GS;
+      float* sL = sCov + GS * LD;
+      float* sW = sL + GS * LD;
+      for (int i = tid; i < GS; i += kTcThreads) sMean[i] = sShift[o + i] + sAcc[kTileCh * kTileCh + o + i] * invM;
+      for (int e = tid; e < GS * GS; e += kTcThreads) {
+        const int i = e / GS, j = e - i * GS, hi = i > j ? i : j, lo = i > j ? j : i;
+        sCov[i * LD + j] = sAcc[(o + hi) * kTileCh + o + lo] * invM -
+                           (sAcc[kTileCh * kTileCh + o + i] * invM) * (sAcc[kTileCh * kTileCh + o + j] * invM);
+      }
+      __syncthreads();
+      fwd_factor_block(gm, ffin, d, g, sMean, sCov, sL, sW, true);
+      fwd_ema_block(gm, ffin, g, &bars.flag);
+    } else {
+      float* sR = scratch;
+      float* sSdz = sR + GS * LD;
+      float* sW = sSdz + GS;
+      float* sT1 = sW + GS * LD;
+      float* sT2 = sT1 + GS * LD;
+      float* sVec = sT2 + GS * LD;
+      for (int e = tid; e < GS * GS; e += kTcThreads) sR[(e / GS) * LD + e % GS] = sAcc[(o + e / GS) * kTileCh + o + e % GS];
+      for (int i = tid; i < GS; i += kTcThreads) sSdz[i] = sAcc[kTileCh * kTileCh + o + i];
+      __syncthreads();
+      bwd_finalize_block(gm, bfin, d, g, sR, sSdz, sW, sT1, sT2, sVec, &bars.flag);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+bool make_map(CUtensorMap* map, const float* base, const Geom& gm) {
+  const cuuint64_t dims[3] = {(cuuint64_t)gm.HW, (cuuint64_t)gm.C, (cuuint64_t)gm.N * gm.D};
+  const cuuint64_t strides[2] = {(cuuint64_t)gm.HW * 4, (cuuint64_t)gm.C * gm.HW * 4};
+  const cuuint32_t box[3] = {kTilePx, kTileCh, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t tc_smem_bytes(int GS, bool two) {
+  const int LD = GS + 1, nacc = kTileCh * kTileCh + kTileCh;
+  const size_t tiles = (size_t)(two ? kStagesBwd * 2 : kStagesStats) * kTileBytes;
+  const size_t fin = sizeof(float) * (size_t)(nacc + (two ? 4 * GS * LD + GS + 3 * GS : GS + 3 * GS * LD));
+  return (tiles > fin ? tiles : fin) + 1024;
+}
+
+}  // namespace
+
+int tc_init() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || fn == nullptr || q != cudaDriverEntryPointSuccess) return e == cudaSuccess ? -1 : (int)e;
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  const int big = (int)tc_smem_bytes(64, true);
+  e = cudaFuncSetAttribute(tc_contract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_contract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  return (int)e;
+}
+
+// The TMA/tcgen05 contraction takes group sizes that tile a 64-channel super-block, rows that TMA can
+// address (16-byte strides and base) and at least one full 32-pixel box per row.
+bool tc_supports(const Geom& gm, int vec) {
+  return gm.GS >= 8 && kTileCh % gm.GS == 0 && vec == 4 && gm.HW >= kTilePx;
+}
+
+int tc_superblocks(const Geom& gm) { return (gm.C + kTileCh - 1) / kTileCh; }
+
+int tc_stats(const float* x, const Geom& gm, int nchunks, const FwdFin& fin, float* partial, int* counters,
+             cudaStream_t st) {
+  CUtensorMap mx;
+  if (!make_map(&mx, x, gm)) return -1;
+  dim3 grid(nchunks, tc_superblocks(gm), gm.D);
+  BwdFin none{};
+  tc_contract_kernel<false><<<grid, kTcThreads, tc_smem_bytes(gm.GS, false), st>>>(mx, mx, x, gm, fin, none, partial, counters);
+  return 0;
+}
+
+int tc_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nchunks, const BwdFin& fin, float* partial,
+                  int* counters, cudaStream_t st) {
+  CUtensorMap mx, mg;
+  if (!make_map(&mx, x, gm) || !make_map(&mg, dout, gm)) return -1;
+  dim3 grid(nchunks, tc_superblocks(gm), gm.D);
+  FwdFin none{};
+  tc_contract_kernel<true><<<grid, kTcThreads, tc_smem_bytes(gm.GS, true), st>>>(mx, mg, x, gm, none, fin, partial, counters);
+  return 0;
+}
+
+}  // namespace dwt
