@@ -1,0 +1,65 @@
+"""World-size-2 data-parallel step on CPU (gloo): the N>1 path of bench.py without a GPU.
+
+The product layers have no CPU path, so the harness model is built on the CPU port of the
+reference layers (oracle/torch_port.py) -- what is under test is the host-side plumbing: one
+process per rank, rank-local whitening statistics (buffers NOT broadcast), gradients averaged by
+the all-reduce, SURVEY.md §8e.
+"""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PICK = ["conv1.weight", "gamma1", "layer1.0.beta2", "layer2.1.gamma3", "layer4.2.conv3.weight", "fc_out.bias"]
+
+
+def _step(rank_seed, ddp):
+    sys.path[:0] = [ROOT]
+    import bench
+    import oracle.torch_port as port
+    from harness.synth import synth_batch
+    torch.manual_seed(0)
+    torch.set_num_threads(2)
+    model = bench.build_model(port, torch.device("cpu"), "modules")
+    net = torch.nn.parallel.DistributedDataParallel(model, broadcast_buffers=False) if ddp else model
+    opt = bench.make_optimizer(model)
+    mec = port.MinEntropyConsensusLoss(bench.NUM_CLASSES, "cpu")
+    images, labels = synth_batch(seed=rank_seed, per_domain=1, size=64)
+    opt.zero_grad(set_to_none=True)
+    logits = net(images)
+    s, t, a = torch.split(logits, 1, dim=0)
+    loss = torch.nn.functional.nll_loss(torch.log_softmax(s, 1), labels) + bench.LAMBDA_MEC * mec(t, a)
+    loss.backward()
+    params = dict(model.named_parameters())
+    return {k: params[k].grad.clone() for k in PICK}, model.state_dict()["bns1.wh.running_mean"].clone()
+
+
+def _worker(rank, world, port_no, out_dir):
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port_no}", rank=rank, world_size=world)
+    grads, buf = _step(100 + rank, ddp=True)
+    torch.save({"grads": grads, "buf": buf}, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_step_averages_gradients_and_keeps_statistics_local(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port_no = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port_no, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(tmp_path / f"rank{r}.pt") for r in range(2))
+    g0, b0 = _step(100, ddp=False)
+    g1, b1 = _step(101, ddp=False)
+    for k in PICK:
+        assert torch.allclose(r0["grads"][k], r1["grads"][k], rtol=0, atol=0), k          # identical after all-reduce
+        mean = 0.5 * (g0[k] + g1[k])
+        assert torch.allclose(r0["grads"][k], mean, rtol=1e-4, atol=1e-6 * mean.abs().max().item()), k
+    # whitening statistics stay rank-local: each rank's buffer equals its own single-process run
+    assert torch.allclose(r0["buf"], b0, atol=1e-6) and torch.allclose(r1["buf"], b1, atol=1e-6)
+    assert not torch.allclose(r0["buf"], r1["buf"], atol=1e-6)
