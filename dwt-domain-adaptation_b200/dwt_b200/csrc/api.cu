@@ -273,8 +273,8 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
     Launch l(p.small ? "small_stats" : (tc ? "tc_stats" : "tiled_stats"), &p.gm, E, st);
     if (p.small) dwt::small_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
     else if (tc) {
-      if (dwt::tc_stats(x, p.gm, tc_chunks(p.gm), fin, w.partial, w.counters, st) != 0)
-        return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed");
+      if (int cr = dwt::tc_stats(x, p.gm, tc_chunks(p.gm), fin, w.partial, w.counters, st))
+        return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed (CUresult %d) x=%p N=%d C=%d HW=%d D=%d", cr, (const void*)x, p.gm.N, p.gm.C, p.gm.HW, p.gm.D);
     } else dwt::tiled_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
   } else {
     Launch l("eval_prep", &p.gm, 0.0, st);
@@ -323,8 +323,8 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
     Launch l(p.small ? "small_bwd_reduce" : (tc ? "tc_bwd_reduce" : "tiled_bwd_reduce"), &p.gm, 2 * E, st);
     if (p.small) dwt::small_bwd_reduce(x, dout, p.gm, p.vec, fin, beta, w.partial, w.counters, st);
     else if (tc) {
-      if (dwt::tc_bwd_reduce(x, dout, p.gm, tc_chunks(p.gm), fin, w.partial, w.counters, st) != 0)
-        return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed");
+      if (int cr = dwt::tc_bwd_reduce(x, dout, p.gm, tc_chunks(p.gm), fin, w.partial, w.counters, st))
+        return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed (CUresult %d) x=%p dout=%p N=%d C=%d HW=%d D=%d", cr, (const void*)x, (const void*)dout, p.gm.N, p.gm.C, p.gm.HW, p.gm.D);
     } else dwt::tiled_bwd_reduce(x, dout, p.gm, p.vec, fin, w.partial, w.counters, st);
   } else {
     Launch l("bwd_prep", &p.gm, 0.0, st);

@@ -359,14 +359,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 
-bool make_map(CUtensorMap* map, const float* base, const Geom& gm) {
+int make_map(CUtensorMap* map, const float* base, const Geom& gm) {
   const cuuint64_t dims[3] = {(cuuint64_t)gm.HW, (cuuint64_t)gm.C, (cuuint64_t)gm.N * gm.D};
   const cuuint64_t strides[2] = {(cuuint64_t)gm.HW * 4, (cuuint64_t)gm.C * gm.HW * 4};
   const cuuint32_t box[3] = {kTilePx, kTileCh, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  return g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return (int)g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
 size_t tc_smem_bytes(int GS, bool two) {
@@ -392,8 +392,10 @@ int tc_init() {
 
 // The TMA/tcgen05 contraction takes group sizes that tile a 64-channel super-block, rows that TMA can
 // address (16-byte strides and base) and at least one full 32-pixel box per row.
+// TF32 operands are rounded to nearest, so product errors are zero-mean and shrink as 1/sqrt(M); below a
+// few thousand samples per channel they do not, and the (exact fp32, FFMA) tiled kernels take the call.
 bool tc_supports(const Geom& gm, int vec) {
-  return gm.GS >= 8 && kTileCh % gm.GS == 0 && vec == 4 && gm.HW >= kTilePx;
+  return gm.GS >= 8 && kTileCh % gm.GS == 0 && vec == 4 && gm.HW >= kTilePx && (long long)gm.N * gm.HW >= 4096;
 }
 
 int tc_superblocks(const Geom& gm) { return (gm.C + kTileCh - 1) / kTileCh; }
@@ -401,7 +403,8 @@ int tc_superblocks(const Geom& gm) { return (gm.C + kTileCh - 1) / kTileCh; }
 int tc_stats(const float* x, const Geom& gm, int nchunks, const FwdFin& fin, float* partial, int* counters,
              cudaStream_t st) {
   CUtensorMap mx;
-  if (!make_map(&mx, x, gm)) return -1;
+  cudaFree(nullptr);        // bind the primary context to this thread (autograd workers call in cold)
+  if (int rc = make_map(&mx, x, gm)) return rc;
   dim3 grid(nchunks, tc_superblocks(gm), gm.D);
   BwdFin none{};
   tc_contract_kernel<false><<<grid, kTcThreads, tc_smem_bytes(gm.GS, false), st>>>(mx, mx, x, gm, fin, none, partial, counters);
@@ -411,7 +414,9 @@ int tc_stats(const float* x, const Geom& gm, int nchunks, const FwdFin& fin, flo
 int tc_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nchunks, const BwdFin& fin, float* partial,
                   int* counters, cudaStream_t st) {
   CUtensorMap mx, mg;
-  if (!make_map(&mx, x, gm) || !make_map(&mg, dout, gm)) return -1;
+  cudaFree(nullptr);        // bind the primary context to this thread (autograd workers call in cold)
+  if (int rc = make_map(&mx, x, gm)) return rc;
+  if (int rc = make_map(&mg, dout, gm)) return rc;
   dim3 grid(nchunks, tc_superblocks(gm), gm.D);
   FwdFin none{};
   tc_contract_kernel<true><<<grid, kTcThreads, tc_smem_bytes(gm.GS, true), st>>>(mx, mg, x, gm, none, fin, partial, counters);

@@ -89,6 +89,8 @@ ORACLE_CASES = [   # N, C, H, W, gs
     (6, 128, 28, 28, 64),     # microbench group size
     (12, 64, 20, 20, 32),
     (9, 48, 10, 10, 16),
+    (48, 48, 10, 10, 16),     # tensor-core contraction with a partial 64-channel super-block (TMA zero fill)
+    (20, 192, 16, 16, 8),     # tensor-core contraction, 8 groups per super-block
     (5, 24, 7, 7, 8),         # tiled path, HW % 4 != 0
     (6, 36, 8, 8, 12),        # group size not a power of two
 ]
