@@ -137,6 +137,8 @@ struct Workspace {
   float* save_cov;    // [D*G*GS*GS]
   float* coef;        // [D*G*(2*GS*GS+GS)]
   float* dgb_part;    // [D*2*C]
+  float* gram;        // [D*SB*(64*64+64)]  reduced moments of the tensor-core contraction
+  float* shift;       // [D*SB*64]          pilot shift of every channel
   size_t bytes;
 };
 
@@ -169,6 +171,9 @@ Workspace carve(void* base, int64_t C, int GS, int D) {
   w.save_cov = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * GS * GS));
   w.coef = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * dwt::coef_stride(GS)));
   w.dgb_part = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * 2 * C));
+  const size_t SBn = (size_t)((C + 63) / 64);
+  w.gram = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * SBn * (64 * 64 + 64)));
+  w.shift = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * SBn * 64));
   w.bytes = off;
   return w;
 }
@@ -273,13 +278,20 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
     Launch l(p.small ? "small_stats" : (tc ? "tc_stats" : "tiled_stats"), &p.gm, E, st);
     if (p.small) dwt::small_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
     else if (tc) {
-      if (int cr = dwt::tc_stats(x, p.gm, tc_chunks(p.gm), fin, w.partial, w.counters, st))
+      if (int cr = dwt::tc_stats(x, p.gm, tc_chunks(p.gm), w.shift, w.partial, st))
         return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed (CUresult %d) x=%p N=%d C=%d HW=%d D=%d", cr, (const void*)x, p.gm.N, p.gm.C, p.gm.HW, p.gm.D);
     } else dwt::tiled_stats(x, p.gm, p.vec, fin, w.partial, w.counters, st);
   } else {
     Launch l("eval_prep", &p.gm, 0.0, st);
     if (p.small) dwt::small_eval_prep(p.gm, fin, st);
+    else if (tc) dwt::dense_fwd_factor(nullptr, nullptr, p.gm, fin, st);
     else dwt::tiled_eval_prep(p.gm, fin, st);
+  }
+  if (tc && mode == DWT_MODE_TRAIN) {
+    if (int rc = check_launch("tensor-core statistics kernel")) return rc;
+    Launch l("dense_fwd_finalize", &p.gm, 0.0, st);
+    dwt::dense_partial_reduce(w.partial, tc_chunks(p.gm), dwt::tc_superblocks(p.gm) * D, w.gram, st);
+    dwt::dense_fwd_factor(w.gram, w.shift, p.gm, fin, st);
   }
   if (int rc = check_launch("whitening statistics kernel")) return rc;
   {
@@ -323,13 +335,20 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
     Launch l(p.small ? "small_bwd_reduce" : (tc ? "tc_bwd_reduce" : "tiled_bwd_reduce"), &p.gm, 2 * E, st);
     if (p.small) dwt::small_bwd_reduce(x, dout, p.gm, p.vec, fin, beta, w.partial, w.counters, st);
     else if (tc) {
-      if (int cr = dwt::tc_bwd_reduce(x, dout, p.gm, tc_chunks(p.gm), fin, w.partial, w.counters, st))
+      if (int cr = dwt::tc_bwd_reduce(x, dout, p.gm, tc_chunks(p.gm), save_mean, w.partial, st))
         return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed (CUresult %d) x=%p dout=%p N=%d C=%d HW=%d D=%d", cr, (const void*)x, (const void*)dout, p.gm.N, p.gm.C, p.gm.HW, p.gm.D);
     } else dwt::tiled_bwd_reduce(x, dout, p.gm, p.vec, fin, w.partial, w.counters, st);
   } else {
     Launch l("bwd_prep", &p.gm, 0.0, st);
     if (p.small) dwt::small_bwd_prep(p.gm, fin, st);
+    else if (tc) dwt::dense_bwd_coef(nullptr, p.gm, fin, st);
     else dwt::tiled_bwd_prep(p.gm, fin, st);
+  }
+  if (tc && need_reduce) {
+    if (int rc = check_launch("tensor-core backward reduction kernel")) return rc;
+    Launch l("dense_bwd_finalize", &p.gm, 0.0, st);
+    dwt::dense_partial_reduce(w.partial, tc_chunks(p.gm), dwt::tc_superblocks(p.gm) * D, w.gram, st);
+    dwt::dense_bwd_coef(w.gram, p.gm, fin, st);
   }
   if (int rc = check_launch("whitening backward reduction kernel")) return rc;
   {

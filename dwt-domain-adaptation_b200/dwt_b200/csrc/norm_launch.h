@@ -36,10 +36,15 @@ void tiled_bwd_apply(const float* x, const float* dout, float* dx, const Geom& g
 int tc_init();      // driver entry point for cuTensorMapEncodeTiled + shared-memory opt-in; 0 on success
 bool tc_supports(const Geom& gm, int vec);
 int tc_superblocks(const Geom& gm);
-int tc_stats(const float* x, const Geom& gm, int nchunks, const FwdFin& fin, float* partial, int* counters,
-             cudaStream_t st);
-int tc_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nchunks, const BwdFin& fin, float* partial,
-                  int* counters, cudaStream_t st);
+int tc_stats(const float* x, const Geom& gm, int nchunks, float* shift, float* partial, cudaStream_t st);
+int tc_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nchunks, const float* save_mean,
+                  float* partial, cudaStream_t st);
+
+// dense per-group algebra behind the contraction (norm_dense.cu)
+int dense_init();
+void dense_partial_reduce(const float* partial, int nchunks, int problems, float* gram, cudaStream_t st);
+void dense_fwd_factor(const float* gram, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st);
+void dense_bwd_coef(const float* rgram, const Geom& gm, const BwdFin& fin, cudaStream_t st);
 
 // MEC loss (mec.cu)
 void mec_launch(const float* x, const float* y, int N, int K, float* loss, float* gx, float* gy, cudaStream_t st);

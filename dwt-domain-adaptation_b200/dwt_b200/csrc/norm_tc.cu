@@ -19,9 +19,9 @@
 //               reference's transposing copy, whitening.py:46, disappears), fp32 accumulator in TMEM;
 //               tcgen05.commit releases the stage back to the producer.
 //   epilogue    tcgen05.ld the 64x64 accumulator (M=64 layout: row r -> lane 32*(r/16) + r%16),
-//               per-CTA partial -> global, last-arriving CTA of the super-block reduces the partials
-//               in fixed order and runs the block-cooperative Cholesky / inverse / EMA (forward) or
-//               the coefficient algebra (backward) of dwt_common.cuh.
+//               per-CTA partial -> global.  The fixed-order reduction of the partials and the dense
+//               algebra (Cholesky / inverse / EMA, or the backward coefficients) run as the small
+//               follow-up launches of norm_dense.cu.
 //
 // Reference: utils/whitening.py:46-47 (/root/reference) and its autograd transpose.
 #include <cuda.h>
@@ -173,8 +173,8 @@ __device__ __forceinline__ void transform_tile(float* tile, int tt, const float 
 template <bool TWO>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
-                   const float* __restrict__ x, const Geom gm, const FwdFin ffin, const BwdFin bfin,
-                   float* __restrict__ partial, int* counters) {
+                   const float* __restrict__ x, const Geom gm, const float* __restrict__ save_mean,
+                   float* __restrict__ shift_out, float* __restrict__ partial) {
   constexpr int STAGES = TWO ? kStagesBwd : kStagesStats;
   constexpr int NT = TWO ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -197,7 +197,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const int r = tid - 64, c = ch0 + r;
     float sh = 0.f;
     if (c < gm.C) {
-      if (TWO) sh = bfin.save_mean[(size_t)d * gm.C + c];
+      if (TWO) sh = save_mean[(size_t)d * gm.C + c];
       else {
         const int np = gm.HW < 32 ? gm.HW : 32, p0 = ((gm.HW - np) / 2) & ~3;
         const float* px = x + ((size_t)d * gm.N * gm.C + c) * gm.HW + p0;
@@ -207,6 +207,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
     }
     sShift[r] = sh;
+    if (!TWO && blockIdx.x == 0) shift_out[((size_t)d * gridDim.y + sb) * kTileCh + r] = sh;
   }
   tc_fence_before();
   __syncthreads();
@@ -308,47 +309,6 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d); }
 
-  if (!arrive_is_last(counters + d * gridDim.y + sb, gridDim.x, &bars.flag)) return;
-
-  // ===== last CTA of the super-block: fixed-order reduction + finalize of its groups =====
-  float* sAcc = reinterpret_cast<float*>(smem);                       // [64*64 + 64]
-  float* scratch = sAcc + nacc;
-  __syncthreads();
-  reduce_partials(partial + ((size_t)d * gridDim.y + sb) * gridDim.x * nacc, gridDim.x, nacc, sAcc);
-  __syncthreads();
-  const int GS = gm.GS, LD = GS + 1, nb = kTileCh / GS;
-  const float invM = 1.f / gm.M;
-  for (int b = 0; b < nb; ++b) {
-    const int g = sb * nb + b, o = b * GS;
-    if (g >= gm.G) break;
-    if constexpr (!TWO) {
-      float* sMean = scratch;
-      float* sCov = sMean + GS;
-      float* sL = sCov + GS * LD;
-      float* sW = sL + GS * LD;
-      for (int i = tid; i < GS; i += kTcThreads) sMean[i] = sShift[o + i] + sAcc[kTileCh * kTileCh + o + i] * invM;
-      for (int e = tid; e < GS * GS; e += kTcThreads) {
-        const int i = e / GS, j = e - i * GS, hi = i > j ? i : j, lo = i > j ? j : i;
-        sCov[i * LD + j] = sAcc[(o + hi) * kTileCh + o + lo] * invM -
-                           (sAcc[kTileCh * kTileCh + o + i] * invM) * (sAcc[kTileCh * kTileCh + o + j] * invM);
-      }
-      __syncthreads();
-      fwd_factor_block(gm, ffin, d, g, sMean, sCov, sL, sW, true);
-      fwd_ema_block(gm, ffin, g, &bars.flag);
-    } else {
-      float* sR = scratch;
-      float* sSdz = sR + GS * LD;
-      float* sW = sSdz + GS;
-      float* sT1 = sW + GS * LD;
-      float* sT2 = sT1 + GS * LD;
-      float* sVec = sT2 + GS * LD;
-      for (int e = tid; e < GS * GS; e += kTcThreads) sR[(e / GS) * LD + e % GS] = sAcc[(o + e / GS) * kTileCh + o + e % GS];
-      for (int i = tid; i < GS; i += kTcThreads) sSdz[i] = sAcc[kTileCh * kTileCh + o + i];
-      __syncthreads();
-      bwd_finalize_block(gm, bfin, d, g, sR, sSdz, sW, sT1, sT2, sVec, &bars.flag);
-    }
-    __syncthreads();
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -369,12 +329,7 @@ int make_map(CUtensorMap* map, const float* base, const Geom& gm) {
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-size_t tc_smem_bytes(int GS, bool two) {
-  const int LD = GS + 1, nacc = kTileCh * kTileCh + kTileCh;
-  const size_t tiles = (size_t)(two ? kStagesBwd * 2 : kStagesStats) * kTileBytes;
-  const size_t fin = sizeof(float) * (size_t)(nacc + (two ? 4 * GS * LD + GS + 3 * GS : GS + 3 * GS * LD));
-  return (tiles > fin ? tiles : fin) + 1024;
-}
+size_t tc_smem_bytes(bool two) { return (size_t)(two ? kStagesBwd * 2 : kStagesStats) * kTileBytes + 1024; }
 
 }  // namespace
 
@@ -384,9 +339,10 @@ int tc_init() {
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
   if (e != cudaSuccess || fn == nullptr || q != cudaDriverEntryPointSuccess) return e == cudaSuccess ? -1 : (int)e;
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  const int big = (int)tc_smem_bytes(64, true);
-  e = cudaFuncSetAttribute(tc_contract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_contract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  e = cudaFuncSetAttribute(tc_contract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(false));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tc_contract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(true));
+  if (e == cudaSuccess) e = (cudaError_t)dense_init();
   return (int)e;
 }
 
@@ -400,26 +356,24 @@ bool tc_supports(const Geom& gm, int vec) {
 
 int tc_superblocks(const Geom& gm) { return (gm.C + kTileCh - 1) / kTileCh; }
 
-int tc_stats(const float* x, const Geom& gm, int nchunks, const FwdFin& fin, float* partial, int* counters,
-             cudaStream_t st) {
+// partial: [D][SB][nchunks][64*64+64] per-CTA moments;  shift: [D][SB][64] pilot shift of every channel
+int tc_stats(const float* x, const Geom& gm, int nchunks, float* shift, float* partial, cudaStream_t st) {
   CUtensorMap mx;
   cudaFree(nullptr);        // bind the primary context to this thread (autograd workers call in cold)
   if (int rc = make_map(&mx, x, gm)) return rc;
   dim3 grid(nchunks, tc_superblocks(gm), gm.D);
-  BwdFin none{};
-  tc_contract_kernel<false><<<grid, kTcThreads, tc_smem_bytes(gm.GS, false), st>>>(mx, mx, x, gm, fin, none, partial, counters);
+  tc_contract_kernel<false><<<grid, kTcThreads, tc_smem_bytes(false), st>>>(mx, mx, x, gm, nullptr, shift, partial);
   return 0;
 }
 
-int tc_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nchunks, const BwdFin& fin, float* partial,
-                  int* counters, cudaStream_t st) {
+int tc_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nchunks, const float* save_mean,
+                  float* partial, cudaStream_t st) {
   CUtensorMap mx, mg;
-  cudaFree(nullptr);        // bind the primary context to this thread (autograd workers call in cold)
+  cudaFree(nullptr);
   if (int rc = make_map(&mx, x, gm)) return rc;
   if (int rc = make_map(&mg, dout, gm)) return rc;
   dim3 grid(nchunks, tc_superblocks(gm), gm.D);
-  FwdFin none{};
-  tc_contract_kernel<true><<<grid, kTcThreads, tc_smem_bytes(gm.GS, true), st>>>(mx, mg, x, gm, none, fin, partial, counters);
+  tc_contract_kernel<true><<<grid, kTcThreads, tc_smem_bytes(true), st>>>(mx, mg, x, gm, save_mean, nullptr, partial);
   return 0;
 }
 
