@@ -105,6 +105,15 @@ int tc_chunks(const dwt::Geom& g) {
   return n < 1 ? 1 : n;
 }
 
+// persistent CTAs per (domain, super-block) of the tensor-core apply kernels: one CTA per SM
+int tc_apply_ctas(const dwt::Geom& g) {
+  const int problems = dwt::tc_superblocks(g) * g.D;
+  int n = sm_count() / problems;
+  const int64_t tiles = (int64_t)g.N * ((g.HW + 63) / 64);
+  if (n > tiles) n = (int)tiles;
+  return n < 1 ? 1 : n;
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Launch shaping.  Every norm kernel is a single wave of long-lived CTAs: `target` CTAs in total
@@ -295,9 +304,12 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
   }
   if (int rc = check_launch("whitening statistics kernel")) return rc;
   {
-    Launch l(p.small ? "small_apply" : "tiled_apply", &p.gm, 2 * E, st);
+    Launch l(p.small ? "small_apply" : (tc ? "tc_apply" : "tiled_apply"), &p.gm, 2 * E, st);
     if (p.small) dwt::small_apply(x, y, p.gm_ew, p.vec, p.chunks_ew, epi, save_mean, save_w, gamma, beta, st);
-    else dwt::tiled_apply(x, y, p.gm_ew, p.vec, p.chunks_ew, save_mean, save_w, st);
+    else if (tc) {
+      if (int cr = dwt::tc_apply(x, y, p.gm, tc_apply_ctas(p.gm), save_mean, save_w, st))
+        return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed (CUresult %d)", cr);
+    } else dwt::tiled_apply(x, y, p.gm_ew, p.vec, p.chunks_ew, save_mean, save_w, st);
   }
   return check_launch("whitening apply kernel");
 }
@@ -341,20 +353,23 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
   } else {
     Launch l("bwd_prep", &p.gm, 0.0, st);
     if (p.small) dwt::small_bwd_prep(p.gm, fin, st);
-    else if (tc) dwt::dense_bwd_coef(nullptr, p.gm, fin, st);
+    else if (tc) dwt::dense_bwd_coef(nullptr, p.gm, fin, w.shift, st);
     else dwt::tiled_bwd_prep(p.gm, fin, st);
   }
   if (tc && need_reduce) {
     if (int rc = check_launch("tensor-core backward reduction kernel")) return rc;
     Launch l("dense_bwd_finalize", &p.gm, 0.0, st);
     dwt::dense_partial_reduce(w.partial, tc_chunks(p.gm), dwt::tc_superblocks(p.gm) * D, w.gram, st);
-    dwt::dense_bwd_coef(w.gram, p.gm, fin, st);
+    dwt::dense_bwd_coef(w.gram, p.gm, fin, w.shift, st);
   }
   if (int rc = check_launch("whitening backward reduction kernel")) return rc;
   {
-    Launch l(p.small ? "small_bwd_apply" : "tiled_bwd_apply", &p.gm, 3 * E, st);
+    Launch l(p.small ? "small_bwd_apply" : (tc ? "tc_bwd_apply" : "tiled_bwd_apply"), &p.gm, 3 * E, st);
     if (p.small) dwt::small_bwd_apply(x, dout, dx, p.gm_ew, p.vec, p.chunks_ew, epi, w.coef, save_mean, save_w, gamma, beta, st);
-    else dwt::tiled_bwd_apply(x, dout, dx, p.gm_ew, p.vec, p.chunks_ew, w.coef, st);
+    else if (tc) {
+      if (int cr = dwt::tc_bwd_apply(x, dout, dx, p.gm, tc_apply_ctas(p.gm), w.coef, save_mean, w.shift, st))
+        return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed (CUresult %d)", cr);
+    } else dwt::tiled_bwd_apply(x, dout, dx, p.gm_ew, p.vec, p.chunks_ew, w.coef, st);
   }
   return check_launch("whitening backward apply kernel");
 }

@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(256) fwd_factor_kernel(const float* __restrict
 // bwd_coef: grid (G, 1, D), 256 threads.  rgram [D][SB][kNacc] = (R = sum dy xc^T | sdz = sum dy).
 // coef[d][g] = A1 | Bm | cvec  with  dx = A1 dy + Bm x + cvec   (no affine epilogue on this path)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bwd_coef_kernel(const float* __restrict__ rgram, const Geom gm, const BwdFin f) {
+__global__ void __launch_bounds__(256) bwd_coef_kernel(const float* __restrict__ rgram, const Geom gm, const BwdFin f,
+                                                       float* __restrict__ dybar) {
   extern __shared__ __align__(16) float dsm[];
   float* sW = dsm;
   float* sR = sW + kMat;
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(256) bwd_coef_kernel(const float* __restrict__
   for (int i = threadIdx.x; i < GS; i += blockDim.x) {
     sSdz[i] = (G && train) ? G[kSB * kSB + o + i] : 0.f;
     sMu[i] = f.save_mean[(size_t)d * gm.C + g * GS + i];
+    if (dybar) dybar[((size_t)d * SB + sb) * kSB + o + i] = sSdz[i] / gm.M;      // mean_M dy (0 in eval mode)
   }
   __syncthreads();
   float c[4][4];
@@ -352,8 +354,8 @@ void dense_fwd_factor(const float* gram, const float* shift, const Geom& gm, con
 }
 
 // rgram == nullptr: eval mode without affine (A1 = W^T only)
-void dense_bwd_coef(const float* rgram, const Geom& gm, const BwdFin& fin, cudaStream_t st) {
-  bwd_coef_kernel<<<dim3(gm.G, 1, gm.D), 256, kCoefSmem, st>>>(rgram, gm, fin);
+void dense_bwd_coef(const float* rgram, const Geom& gm, const BwdFin& fin, float* dybar, cudaStream_t st) {
+  bwd_coef_kernel<<<dim3(gm.G, 1, gm.D), 256, kCoefSmem, st>>>(rgram, gm, fin, dybar);
 }
 
 }  // namespace dwt

@@ -44,7 +44,14 @@ int tc_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nchunks
 int dense_init();
 void dense_partial_reduce(const float* partial, int nchunks, int problems, float* gram, cudaStream_t st);
 void dense_fwd_factor(const float* gram, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st);
-void dense_bwd_coef(const float* rgram, const Geom& gm, const BwdFin& fin, cudaStream_t st);
+void dense_bwd_coef(const float* rgram, const Geom& gm, const BwdFin& fin, float* dybar, cudaStream_t st);
+
+// TMA + tcgen05 apply path (norm_tc_apply.cu): split-TF32 GEMM of the block-diagonal group matrices
+int tc_apply_init();
+int tc_apply(const float* x, float* y, const Geom& gm, int nctas, const float* save_mean, const float* save_w,
+             cudaStream_t st);
+int tc_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, const float* coef,
+                 const float* save_mean, const float* dybar, cudaStream_t st);
 
 // MEC loss (mec.cu)
 void mec_launch(const float* x, const float* y, int N, int K, float* loss, float* gx, float* gy, cudaStream_t st);

@@ -1,0 +1,309 @@
+// Tensor-core path for the two APPLY passes when groups are large (group size 8..64):
+//
+//   apply       y  = W (x - mean)                               one input tensor
+//   bwd_apply   dx = A1 (dy - mean_M dy) + Bm (x - mean)        two input tensors
+//
+// Per 64-channel super-block the per-group matrices form one block-diagonal 64x64 matrix M, and a
+// [64 ch x 64 px] tile of the NCHW tensor is out = M * tile: a GEMM whose B operand is the tile exactly
+// as TMA lands it (rows = channels = K, pixels contiguous = MN-major), so again nothing is transposed.
+// A single-pass TF32 product is NOT accurate enough here -- each output is one length-64 dot product
+// whose terms can cancel by the condition number of the covariance -- so both operands are split
+// x = hi + lo (hi = RN_tf32(x), lo = RN_tf32(x - hi)) and the four partial products are accumulated in
+// fp32: the matrix halves are STACKED as a 128-row A operand [M_hi ; M_lo], so one M=128 MMA per B half
+// yields rows 0-63 = M_hi*B and rows 64-127 = M_lo*B in TMEM; the epilogue adds the two row halves.
+//
+// CTA = 10 warps, persistent over a contiguous range of 64-pixel tiles of one (domain, super-block):
+//   warp 0     TMA producer (2 boxes of 32 px x 64 ch per input tensor and stage, SWIZZLE_128B)
+//   warp 1     MMA issuer (tcgen05.mma kind::tf32, M=128 N=64 K=8; A K-major, B MN-major), TMEM owner
+//   warps 2-5  transform: in place hi = RN(v - shift[c]), second buffer lo = RN(v - shift[c] - hi)
+//   warps 6-9  epilogue: tcgen05.ld 128 lanes x 64 columns, fold row halves through shared memory,
+//              coalesced 256-byte row stores; TMEM accumulators are double-buffered against the MMA.
+//
+// Reference: the grouped 1x1 convolution at utils/whitening.py:55 (/root/reference) and its backward.
+#include <cuda.h>
+
+#include "dwt_common.cuh"
+#include "norm_launch.h"
+#include "tc_ptx.cuh"
+
+namespace dwt {
+namespace {
+
+using namespace tc;
+
+constexpr int kApThreads = 320;
+constexpr int kBoxPx = 32, kTilePxA = 64, kCh = 64;
+constexpr int kBoxBytes = kCh * kBoxPx * 4;          // 8192
+constexpr int kHalfBytes = 2 * kBoxBytes;            // hi (or lo) of one input: 2 boxes = 16 KB
+constexpr int kInBytes = 2 * kHalfBytes;             // hi + lo of one input = 32 KB
+constexpr int kMatBytes = 2 * 128 * 128;             // stacked [M_hi ; M_lo], 2 K-slabs of 128 rows x 128 B = 32 KB
+constexpr int kStageLd = kTilePxA + 1;               // staging row stride (floats)
+constexpr int kAccCols = 64;                         // TMEM columns per accumulator
+
+struct ApBarriers {
+  uint64_t full[4], ready[4], empty[4];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_slot;
+};
+
+struct ApplyArgs {
+  const float* mats;      // per (domain, group) records
+  int rec_stride;         // floats per record
+  int off[2];             // offset of the matrix applied to input i inside a record
+  const float* shift[2];  // per-channel shift of input i
+  int shift_stride[2];    // floats per domain in shift[i]
+  float* out;
+};
+
+// Build the stacked, hi/lo-split, K-major SWIZZLE_128B image of the block-diagonal 64x64 matrix of
+// this super-block in shared memory.  Element (row i, k): slab k/32, row i (hi) or 64+i (lo).
+__device__ __forceinline__ void build_matrix(uint8_t* dst, const float* mats, int rec_stride, int off, int d, int sb,
+                                             const Geom& gm) {
+  const int GS = gm.GS, nb = kCh / GS;
+  for (int e = threadIdx.x; e < kCh * kCh; e += blockDim.x) {
+    const int i = e >> 6, k = e & 63;
+    float w = 0.f;
+    const int gi = i / GS, gk = k / GS, g = sb * nb + gi;
+    if (gi == gk && g < gm.G) w = __ldg(mats + ((size_t)d * gm.G + g) * rec_stride + off + (i - gi * GS) * GS + (k - gk * GS));
+    const float hi = round_tf32(w), lo = round_tf32(w - hi);
+    const int slab = k >> 5, kc = (k & 31) >> 2, kw = k & 3;
+    uint8_t* base = dst + slab * (128 * 128);
+    *reinterpret_cast<float*>(base + i * 128 + (((kc ^ (i & 7))) << 4) + kw * 4) = hi;
+    const int il = 64 + i;
+    *reinterpret_cast<float*>(base + il * 128 + (((kc ^ (il & 7))) << 4) + kw * 4) = lo;
+  }
+}
+
+// hi/lo split of one landed 32 px x 64 ch box by the 128 transform threads (tt = 0..127).
+__device__ __forceinline__ void split_box(float* hi, float* lo, int tt, const float (&shift)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = tt + 128 * i;                    // 16-byte chunk; row = q >> 3
+    float4 v = reinterpret_cast<float4*>(hi)[q];
+    float e[4] = {v.x - shift[i], v.y - shift[i], v.z - shift[i], v.w - shift[i]}, h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { h[k] = round_tf32(e[k]); l[k] = round_tf32(e[k] - h[k]); }
+    reinterpret_cast<float4*>(hi)[q] = make_float4(h[0], h[1], h[2], h[3]);
+    reinterpret_cast<float4*>(lo)[q] = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+template <int NIN>
+__global__ void __launch_bounds__(kApThreads, 1)
+tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Geom gm,
+                const ApplyArgs args) {
+  constexpr int STAGES = NIN == 1 ? 4 : 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sMat = smem;                                       // NIN x 32 KB
+  uint8_t* sStage = sMat + NIN * kMatBytes;                   // STAGES x NIN x 32 KB
+  float* sOut = reinterpret_cast<float*>(sStage + STAGES * NIN * kInBytes);   // [64][65]
+  __shared__ ApBarriers bars;
+  __shared__ float sShift[2][kCh];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int sb = blockIdx.y, d = blockIdx.z, ch0 = sb * kCh;
+  const int PB = (gm.HW + kTilePxA - 1) / kTilePxA;
+  const long long T = (long long)gm.N * PB;
+  const int t_begin = (int)(T * blockIdx.x / gridDim.x), t_end = (int)(T * (blockIdx.x + 1) / gridDim.x);
+  const int ntiles = t_end - t_begin;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.ready[s], 4); mbar_init(&bars.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_empty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<2 * kAccCols>(&bars.tmem_slot);
+  for (int i = 0; i < NIN; ++i) build_matrix(sMat + i * kMatBytes, args.mats, args.rec_stride, args.off[i], d, sb, gm);
+  if (tid < NIN * kCh) {
+    const int i = tid / kCh, r = tid - i * kCh, c = ch0 + r;
+    sShift[i][r] = (c < gm.C && args.shift[i] != nullptr) ? __ldg(args.shift[i] + (size_t)d * args.shift_stride[i] + c) : 0.f;
+  }
+  fence_proxy_async();              // the matrix image was written by the generic proxy, the MMA reads it asynchronously
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int it = 0; it < ntiles; ++it) {
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(&bars.empty[s], ph ^ 1);
+        const int t = t_begin + it, n = t / PB, pb = t - n * PB;
+        uint8_t* dst = sStage + (size_t)s * NIN * kInBytes;
+        mbar_arrive_expect_tx(&bars.full[s], NIN * kHalfBytes);
+#pragma unroll
+        for (int i = 0; i < NIN; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_3d(dst + i * kInBytes + j * kBoxBytes, i == 0 ? &map0 : &map1, pb * kTilePxA + j * kBoxPx, ch0,
+                        d * gm.N + n, &bars.full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_tf32(128, kTilePxA, true);
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % STAGES, ph = (it / STAGES) & 1, b = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(&bars.ready[s], ph);
+      mbar_wait(&bars.acc_empty[b], aph ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t stage = smem_u32(sStage + (size_t)s * NIN * kInBytes);
+        uint32_t first = 1;
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) {
+          const uint32_t mat = smem_u32(sMat + i * kMatBytes);
+#pragma unroll
+          for (int term = 0; term < 2; ++term) {                 // B = hi half, then lo half
+            const uint32_t bbase = stage + i * kInBytes + term * kHalfBytes;
+#pragma unroll
+            for (int ks = 0; ks < kCh / 8; ++ks) {
+              const uint64_t adesc = make_kmajor_sw128_desc(mat + (ks >> 2) * (128 * 128) + (ks & 3) * 32);
+              const uint64_t bdesc = make_mnmajor_sw128_desc(bbase + ks * 1024, kBoxBytes, 1024);
+              umma_tf32(tmem + b * kAccCols, adesc, bdesc, idesc, first ? 0u : 1u);
+              first = 0;
+            }
+          }
+        }
+        umma_commit(&bars.empty[s]);
+        umma_commit(&bars.acc_full[b]);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ===== transform warps =====
+    const int tt = tid - 64;
+    float sh[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) sh[i][r] = sShift[i][(tt + 128 * r) >> 3];
+    for (int it = 0; it < ntiles; ++it) {
+      const int s = it % STAGES, ph = (it / STAGES) & 1;
+      mbar_wait(&bars.full[s], ph);
+      uint8_t* st = sStage + (size_t)s * NIN * kInBytes;
+#pragma unroll
+      for (int i = 0; i < NIN; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          split_box(reinterpret_cast<float*>(st + i * kInBytes + j * kBoxBytes),
+                    reinterpret_cast<float*>(st + i * kInBytes + kHalfBytes + j * kBoxBytes), tt, sh[i]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.ready[s]);
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int et = tid - 192;                      // 0..127
+    const int quad = warp & 3;                     // TMEM lane quadrant of this warp
+    const int row = quad * 32 + lane;              // accumulator row held by this thread
+    for (int it = 0; it < ntiles; ++it) {
+      const int b = it & 1, aph = (it >> 1) & 1;
+      mbar_wait(&bars.acc_full[b], aph);
+      tc_fence_after();
+      float v[2][32];
+      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + b * kAccCols, v[0]);
+      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + b * kAccCols + 32, v[1]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.acc_empty[b]);          // accumulator drained: MMA may reuse it
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // previous tile's stores have left sOut
+      if (row >= 64) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < 32; ++c) sOut[(row - 64) * kStageLd + h * 32 + c] = v[h][c];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (row < 64) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < 32; ++c) sOut[row * kStageLd + h * 32 + c] += v[h][c];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // coalesced stores: 8 threads per row-quarter... 16 float4 per 64-pixel row, 8 rows per pass
+      const int t = t_begin + it, n = t / PB, pb = t - n * PB, px0 = pb * kTilePxA;
+      float* obase = args.out + ((size_t)(d * gm.N + n) * gm.C + ch0) * gm.HW + px0;
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int r = pass * 8 + (et >> 4), c4 = (et & 15) * 4;
+        if (ch0 + r < gm.C && px0 + c4 < gm.HW) {
+          const float* src = sOut + r * kStageLd + c4;
+          *reinterpret_cast<float4*>(obase + (size_t)r * gm.HW + c4) = make_float4(src[0], src[1], src[2], src[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<2 * kAccCols>(tmem); }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_ap = nullptr;
+
+int make_map_ap(CUtensorMap* map, const float* base, const Geom& gm) {
+  const cuuint64_t dims[3] = {(cuuint64_t)gm.HW, (cuuint64_t)gm.C, (cuuint64_t)gm.N * gm.D};
+  const cuuint64_t strides[2] = {(cuuint64_t)gm.HW * 4, (cuuint64_t)gm.C * gm.HW * 4};
+  const cuuint32_t box[3] = {kBoxPx, kCh, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return (int)g_encode_ap(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+template <int NIN> constexpr size_t ap_smem() {
+  return (size_t)NIN * kMatBytes + (size_t)(NIN == 1 ? 4 : 2) * NIN * kInBytes + sizeof(float) * kCh * kStageLd + 1024;
+}
+
+}  // namespace
+
+int tc_apply_init() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || fn == nullptr || q != cudaDriverEntryPointSuccess) return e == cudaSuccess ? -1 : (int)e;
+  g_encode_ap = reinterpret_cast<EncodeTiledFn>(fn);
+  e = cudaFuncSetAttribute(tc_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ap_smem<1>());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ap_smem<2>());
+  return (int)e;
+}
+
+// y = W (x - mean): W from save_w [D][G][gs*gs], mean from save_mean [D][C]
+int tc_apply(const float* x, float* y, const Geom& gm, int nctas, const float* save_mean, const float* save_w,
+             cudaStream_t st) {
+  CUtensorMap mx;
+  cudaFree(nullptr);
+  if (int rc = make_map_ap(&mx, x, gm)) return rc;
+  ApplyArgs a{};
+  a.mats = save_w; a.rec_stride = gm.GS * gm.GS; a.off[0] = 0; a.off[1] = 0;
+  a.shift[0] = save_mean; a.shift_stride[0] = gm.C; a.shift[1] = nullptr; a.shift_stride[1] = 0;
+  a.out = y;
+  dim3 grid(nctas, (gm.C + kCh - 1) / kCh, gm.D);
+  tc_apply_kernel<1><<<grid, kApThreads, ap_smem<1>(), st>>>(mx, mx, gm, a);
+  return 0;
+}
+
+// dx = A1 (dy - dybar) + Bm (x - mean): coef [D][G][2 gs^2 + gs] = A1 | Bm | cvec, dybar [D][SB*64]
+int tc_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, const float* coef,
+                 const float* save_mean, const float* dybar, cudaStream_t st) {
+  CUtensorMap mx, mg;
+  cudaFree(nullptr);
+  if (int rc = make_map_ap(&mg, dout, gm)) return rc;
+  if (int rc = make_map_ap(&mx, x, gm)) return rc;
+  ApplyArgs a{};
+  a.mats = coef; a.rec_stride = coef_stride(gm.GS); a.off[0] = 0; a.off[1] = gm.GS * gm.GS;
+  a.shift[0] = dybar; a.shift_stride[0] = ((gm.C + kCh - 1) / kCh) * kCh;
+  a.shift[1] = save_mean; a.shift_stride[1] = gm.C;
+  a.out = dx;
+  dim3 grid(nctas, (gm.C + kCh - 1) / kCh, gm.D);
+  tc_apply_kernel<2><<<grid, kApThreads, ap_smem<2>(), st>>>(mg, mx, gm, a);
+  return 0;
+}
+
+}  // namespace dwt
