@@ -132,11 +132,13 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         mbar_wait(&bars.empty[s], ph ^ 1);
         const int t = t_begin + it, n = t / PB, pb = t - n * PB;
         uint8_t* dst = sStage + (size_t)s * NIN * kInBytes;
-        mbar_arrive_expect_tx(&bars.full[s], NIN * kHalfBytes);
+        // the second 32-pixel box of the tile may lie entirely past the row end: do not issue it (its
+        // columns are never stored, whatever the stale shared memory holds)
+        const int nbox = (pb * kTilePxA + kBoxPx < gm.HW) ? 2 : 1;
+        mbar_arrive_expect_tx(&bars.full[s], NIN * nbox * kBoxBytes);
 #pragma unroll
         for (int i = 0; i < NIN; ++i)
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
+          for (int j = 0; j < nbox; ++j)
             tma_load_3d(dst + i * kInBytes + j * kBoxBytes, i == 0 ? &map0 : &map1, pb * kTilePxA + j * kBoxPx, ch0,
                         d * gm.N + n, &bars.full[s]);
       }
