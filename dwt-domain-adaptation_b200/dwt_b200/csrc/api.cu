@@ -105,10 +105,10 @@ int tc_chunks(const dwt::Geom& g) {
   return n < 1 ? 1 : n;
 }
 
-// persistent CTAs per (domain, super-block) of the tensor-core apply kernels: one CTA per SM
-int tc_apply_ctas(const dwt::Geom& g) {
+// persistent CTAs per (domain, super-block) of the tensor-core apply kernels: per_sm CTAs per SM
+int tc_apply_ctas(const dwt::Geom& g, int per_sm) {
   const int problems = dwt::tc_superblocks(g) * g.D;
-  int n = sm_count() / problems;
+  int n = per_sm * sm_count() / problems;
   const int64_t tiles = (int64_t)g.N * ((g.HW + 63) / 64);
   if (n > tiles) n = (int)tiles;
   return n < 1 ? 1 : n;
@@ -307,7 +307,7 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
     Launch l(p.small ? "small_apply" : (tc ? "tc_apply" : "tiled_apply"), &p.gm, 2 * E, st);
     if (p.small) dwt::small_apply(x, y, p.gm_ew, p.vec, p.chunks_ew, epi, save_mean, save_w, gamma, beta, st);
     else if (tc) {
-      if (int cr = dwt::tc_apply(x, y, p.gm, tc_apply_ctas(p.gm), save_mean, save_w, st))
+      if (int cr = dwt::tc_apply(x, y, p.gm, tc_apply_ctas(p.gm, 2), save_mean, save_w, st))
         return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed (CUresult %d)", cr);
     } else dwt::tiled_apply(x, y, p.gm_ew, p.vec, p.chunks_ew, save_mean, save_w, st);
   }
@@ -367,7 +367,7 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
     Launch l(p.small ? "small_bwd_apply" : (tc ? "tc_bwd_apply" : "tiled_bwd_apply"), &p.gm, 3 * E, st);
     if (p.small) dwt::small_bwd_apply(x, dout, dx, p.gm_ew, p.vec, p.chunks_ew, epi, w.coef, save_mean, save_w, gamma, beta, st);
     else if (tc) {
-      if (int cr = dwt::tc_bwd_apply(x, dout, dx, p.gm, tc_apply_ctas(p.gm), w.coef, save_mean, w.shift, st))
+      if (int cr = dwt::tc_bwd_apply(x, dout, dx, p.gm, tc_apply_ctas(p.gm, 1), w.coef, save_mean, w.shift, st))
         return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed (CUresult %d)", cr);
     } else dwt::tiled_bwd_apply(x, dout, dx, p.gm_ew, p.vec, p.chunks_ew, w.coef, st);
   }

@@ -10,14 +10,14 @@
 // whose terms can cancel by the condition number of the covariance -- so both operands are split
 // x = hi + lo (hi = RN_tf32(x), lo = RN_tf32(x - hi)) and the four partial products are accumulated in
 // fp32: the matrix halves are STACKED as a 128-row A operand [M_hi ; M_lo], so one M=128 MMA per B half
-// yields rows 0-63 = M_hi*B and rows 64-127 = M_lo*B in TMEM; the epilogue adds the two row halves.
+// yields M_hi*B and M_lo*B rows in TMEM; the epilogue adds the two row halves.
 //
 // CTA = 10 warps, persistent over a contiguous range of 64-pixel tiles of one (domain, super-block):
 //   warp 0     TMA producer (2 boxes of 32 px x 64 ch per input tensor and stage, SWIZZLE_128B)
-//   warp 1     MMA issuer (tcgen05.mma kind::tf32, M=128 N=64 K=8; A K-major, B MN-major), TMEM owner
+//   warp 1     MMA issuer (tcgen05.mma kind::tf32, M=128 N=64 K=8; A resident in TMEM, B MN-major), TMEM owner
 //   warps 2-5  transform: in place hi = RN(v - shift[c]), second buffer lo = RN(v - shift[c] - hi)
-//   warps 6-9  epilogue: tcgen05.ld 128 lanes x 64 columns, fold row halves through shared memory,
-//              coalesced 256-byte row stores; TMEM accumulators are double-buffered against the MMA.
+//   warps 6-9  epilogue: tcgen05.ld 128 lanes x 64 columns, fold the hi/lo row halves with one shuffle,
+//              256-byte row stores; TMEM accumulators are double-buffered against the MMA.
 //
 // Reference: the grouped 1x1 convolution at utils/whitening.py:55 (/root/reference) and its backward.
 #include <cuda.h>
@@ -36,12 +36,12 @@ constexpr int kBoxPx = 32, kTilePxA = 64, kCh = 64;
 constexpr int kBoxBytes = kCh * kBoxPx * 4;          // 8192
 constexpr int kHalfBytes = 2 * kBoxBytes;            // hi (or lo) of one input: 2 boxes = 16 KB
 constexpr int kInBytes = 2 * kHalfBytes;             // hi + lo of one input = 32 KB
-constexpr int kMatBytes = 2 * 128 * 128;             // stacked [M_hi ; M_lo], 2 K-slabs of 128 rows x 128 B = 32 KB
-constexpr int kStageLd = kTilePxA + 1;               // staging row stride (floats)
-constexpr int kAccCols = 64;                         // TMEM columns per accumulator
+constexpr int kAccCols = 64;                         // TMEM columns per accumulator / per matrix
+constexpr int kTmemAlloc = 256;                      // 2 accumulators + up to 2 resident matrices
+constexpr int kMaxStages = 4;
 
 struct ApBarriers {
-  uint64_t full[4], ready[4], empty[4];
+  uint64_t full[kMaxStages], ready[kMaxStages], empty[kMaxStages];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_slot;
 };
@@ -54,25 +54,6 @@ struct ApplyArgs {
   int shift_stride[2];    // floats per domain in shift[i]
   float* out;
 };
-
-// Build the stacked, hi/lo-split, K-major SWIZZLE_128B image of the block-diagonal 64x64 matrix of
-// this super-block in shared memory.  Element (row i, k): slab k/32, row i (hi) or 64+i (lo).
-__device__ __forceinline__ void build_matrix(uint8_t* dst, const float* mats, int rec_stride, int off, int d, int sb,
-                                             const Geom& gm) {
-  const int GS = gm.GS, nb = kCh / GS;
-  for (int e = threadIdx.x; e < kCh * kCh; e += blockDim.x) {
-    const int i = e >> 6, k = e & 63;
-    float w = 0.f;
-    const int gi = i / GS, gk = k / GS, g = sb * nb + gi;
-    if (gi == gk && g < gm.G) w = __ldg(mats + ((size_t)d * gm.G + g) * rec_stride + off + (i - gi * GS) * GS + (k - gk * GS));
-    const float hi = round_tf32(w), lo = round_tf32(w - hi);
-    const int slab = k >> 5, kc = (k & 31) >> 2, kw = k & 3;
-    uint8_t* base = dst + slab * (128 * 128);
-    *reinterpret_cast<float*>(base + i * 128 + (((kc ^ (i & 7))) << 4) + kw * 4) = hi;
-    const int il = 64 + i;
-    *reinterpret_cast<float*>(base + il * 128 + (((kc ^ (il & 7))) << 4) + kw * 4) = lo;
-  }
-}
 
 // hi/lo split of one landed 32 px x 64 ch box by the 128 transform threads (tt = 0..127).
 __device__ __forceinline__ void split_box(float* hi, float* lo, int tt, const float (&shift)[4]) {
@@ -88,16 +69,18 @@ __device__ __forceinline__ void split_box(float* hi, float* lo, int tt, const fl
   }
 }
 
+// The A operand lives in TENSOR MEMORY for the whole kernel (it is the same for every tile; reading
+// it from shared memory on every MMA was the largest shared-memory consumer of the first version).
+// Row order: TMEM lane 32q + l holds channel 16q + (l & 15), the hi part for l < 16 and the lo part
+// for l >= 16, so the two halves that must be added end up 16 lanes apart IN THE SAME WARP and the
+// epilogue folds them with one shuffle per value -- no shared-memory staging at all.
 template <int NIN>
 __global__ void __launch_bounds__(kApThreads, 1)
 tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Geom gm,
                 const ApplyArgs args) {
-  constexpr int STAGES = NIN == 1 ? 4 : 2;
+  constexpr int STAGES = 3;       // NIN = 1: 97 KB -> two CTAs per SM; NIN = 2: 193 KB -> one
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sMat = smem;                                       // NIN x 32 KB
-  uint8_t* sStage = sMat + NIN * kMatBytes;                   // STAGES x NIN x 32 KB
-  float* sOut = reinterpret_cast<float*>(sStage + STAGES * NIN * kInBytes);   // [64][65]
+  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ ApBarriers bars;
   __shared__ float sShift[2][kCh];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
@@ -112,17 +95,41 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<2 * kAccCols>(&bars.tmem_slot);
-  for (int i = 0; i < NIN; ++i) build_matrix(sMat + i * kMatBytes, args.mats, args.rec_stride, args.off[i], d, sb, gm);
+  if (warp == 1) tmem_alloc<kTmemAlloc>(&bars.tmem_slot);
   if (tid < NIN * kCh) {
     const int i = tid / kCh, r = tid - i * kCh, c = ch0 + r;
     sShift[i][r] = (c < gm.C && args.shift[i] != nullptr) ? __ldg(args.shift[i] + (size_t)d * args.shift_stride[i] + c) : 0.f;
   }
-  fence_proxy_async();              // the matrix image was written by the generic proxy, the MMA reads it asynchronously
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_slot;
+  const uint32_t tmem_acc = tmem, tmem_mat = tmem + 2 * kAccCols;
+
+  if (warp >= 6) {
+    // epilogue warps first park the split matrices in tensor memory
+    const int quad = warp & 3, i = 16 * quad + (lane & 15), GS = gm.GS, gi = i / GS, g = sb * (kCh / GS) + gi;
+    const bool lo_half = lane >= 16;
+    for (int m = 0; m < NIN; ++m) {
+      const float* rec = args.mats + ((size_t)d * gm.G + (g < gm.G ? g : 0)) * args.rec_stride + args.off[m] + (i - gi * GS) * GS;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int k = h * 32 + c;
+          float w = 0.f;
+          if (g < gm.G && k / GS == gi) w = __ldg(rec + (k - gi * GS));
+          const float hi = round_tf32(w);
+          v[c] = lo_half ? round_tf32(w - hi) : hi;
+        }
+        tmem_st32(tmem_mat + m * kAccCols + ((uint32_t)(quad * 32) << 16) + h * 32, v);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -156,15 +163,13 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         uint32_t first = 1;
 #pragma unroll
         for (int i = 0; i < NIN; ++i) {
-          const uint32_t mat = smem_u32(sMat + i * kMatBytes);
 #pragma unroll
           for (int term = 0; term < 2; ++term) {                 // B = hi half, then lo half
             const uint32_t bbase = stage + i * kInBytes + term * kHalfBytes;
 #pragma unroll
             for (int ks = 0; ks < kCh / 8; ++ks) {
-              const uint64_t adesc = make_kmajor_sw128_desc(mat + (ks >> 2) * (128 * 128) + (ks & 3) * 32);
               const uint64_t bdesc = make_mnmajor_sw128_desc(bbase + ks * 1024, kBoxBytes, 1024);
-              umma_tf32(tmem + b * kAccCols, adesc, bdesc, idesc, first ? 0u : 1u);
+              umma_tf32_ts(tmem_acc + b * kAccCols, tmem_mat + i * kAccCols + ks * 8, bdesc, idesc, first ? 0u : 1u);
               first = 0;
             }
           }
@@ -198,50 +203,38 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     }
   } else {
     // ===== epilogue warps =====
-    const int et = tid - 192;                      // 0..127
     const int quad = warp & 3;                     // TMEM lane quadrant of this warp
-    const int row = quad * 32 + lane;              // accumulator row held by this thread
+    const int ch = ch0 + 16 * quad + (lane & 15);  // channel whose hi (lane<16) / lo (lane>=16) row this thread reads
     for (int it = 0; it < ntiles; ++it) {
       const int b = it & 1, aph = (it >> 1) & 1;
       mbar_wait(&bars.acc_full[b], aph);
       tc_fence_after();
       float v[2][32];
-      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + b * kAccCols, v[0]);
-      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + b * kAccCols + 32, v[1]);
+      tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + b * kAccCols, v[0]);
+      tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + b * kAccCols + 32, v[1]);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.acc_empty[b]);          // accumulator drained: MMA may reuse it
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // previous tile's stores have left sOut
-      if (row >= 64) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int c = 0; c < 32; ++c) sOut[(row - 64) * kStageLd + h * 32 + c] = v[h][c];
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (row < 64) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int c = 0; c < 32; ++c) sOut[row * kStageLd + h * 32 + c] += v[h][c];
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      // coalesced stores: 8 threads per row-quarter... 16 float4 per 64-pixel row, 8 rows per pass
+        for (int c = 0; c < 32; ++c) v[h][c] += __shfl_down_sync(0xffffffffu, v[h][c], 16);
       const int t = t_begin + it, n = t / PB, pb = t - n * PB, px0 = pb * kTilePxA;
-      float* obase = args.out + ((size_t)(d * gm.N + n) * gm.C + ch0) * gm.HW + px0;
+      if (lane < 16 && ch < gm.C) {
+        float* orow = args.out + ((size_t)(d * gm.N + n) * gm.C + ch) * gm.HW + px0;
 #pragma unroll
-      for (int pass = 0; pass < 8; ++pass) {
-        const int r = pass * 8 + (et >> 4), c4 = (et & 15) * 4;
-        if (ch0 + r < gm.C && px0 + c4 < gm.HW) {
-          const float* src = sOut + r * kStageLd + c4;
-          *reinterpret_cast<float4*>(obase + (size_t)r * gm.HW + c4) = make_float4(src[0], src[1], src[2], src[3]);
-        }
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            if (px0 + h * 32 + 4 * c4 < gm.HW)
+              *reinterpret_cast<float4*>(orow + h * 32 + 4 * c4) =
+                  make_float4(v[h][4 * c4], v[h][4 * c4 + 1], v[h][4 * c4 + 2], v[h][4 * c4 + 3]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc<2 * kAccCols>(tmem); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<kTmemAlloc>(tmem); }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -259,9 +252,7 @@ int make_map_ap(CUtensorMap* map, const float* base, const Geom& gm) {
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-template <int NIN> constexpr size_t ap_smem() {
-  return (size_t)NIN * kMatBytes + (size_t)(NIN == 1 ? 4 : 2) * NIN * kInBytes + sizeof(float) * kCh * kStageLd + 1024;
-}
+template <int NIN> constexpr size_t ap_smem() { return (size_t)3 * NIN * kInBytes + 1024; }
 
 }  // namespace
 
