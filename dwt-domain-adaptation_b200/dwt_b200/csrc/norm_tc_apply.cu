@@ -13,7 +13,8 @@
 // yields M_hi*B and M_lo*B rows in TMEM; the epilogue adds the two row halves.
 //
 // CTA = 10 warps, persistent over a contiguous range of 64-pixel tiles of one (domain, super-block):
-//   warp 0     TMA producer (2 boxes of 32 px x 64 ch per input tensor and stage, SWIZZLE_128B)
+//   warp 0     TMA producer (2 boxes of 32 px x 64 ch per input tensor and stage, SWIZZLE_128B_ATOM_32B:
+//              the only layout the tensor core takes for an MN-major tf32 operand)
 //   warp 1     MMA issuer (tcgen05.mma kind::tf32, M=128 N=64 K=8; A resident in TMEM, B MN-major), TMEM owner
 //   warps 2-5  transform: in place hi = RN(v - shift[c]), second buffer lo = RN(v - shift[c] - hi)
 //   warps 6-9  epilogue: tcgen05.ld 128 lanes x 64 columns, fold the hi/lo row halves with one shuffle,
@@ -168,7 +169,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
             const uint32_t bbase = stage + i * kInBytes + term * kHalfBytes;
 #pragma unroll
             for (int ks = 0; ks < kCh / 8; ++ks) {
-              const uint64_t bdesc = make_mnmajor_sw128_desc(bbase + ks * 1024, kBoxBytes, 1024);
+              const uint64_t bdesc = make_mnmajor_sw128_32b_desc(bbase + ks * 1024, kBoxBytes, 512);
               umma_tf32_ts(tmem_acc + b * kAccCols, tmem_mat + i * kAccCols + ks * 8, bdesc, idesc, first ? 0u : 1u);
               first = 0;
             }
@@ -248,7 +249,7 @@ int make_map_ap(CUtensorMap* map, const float* base, const Geom& gm) {
   const cuuint32_t box[3] = {kBoxPx, kCh, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   return (int)g_encode_ap(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 

@@ -102,11 +102,14 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// MN-major SWIZZLE_128B descriptor: 8 K-rows x 128 B atoms; LBO = stride between 32-element blocks
-// along M/N, SBO = stride between 8-row groups along K.
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// MN-major descriptor for 32-bit (tf32) operands.  The ONLY shared-memory layout the tensor core accepts
+// for MN-major tf32 is SWIZZLE_128B_BASE32B (cute::UMMA::Layout_MN_SW128_32B_Atom, layout type 1):
+// rows of 128 B (32 elements along M/N), 32-byte chunks XOR-swizzled by (row & 3), K atoms of 4 rows.
+// TMA writes exactly this with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = stride between 32-element
+// blocks along M/N, SBO = stride between 4-row groups along K.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_32b_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+         ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, A K-major, M x N;
 // b_mn_major selects an MN-major (transposed) B operand.
