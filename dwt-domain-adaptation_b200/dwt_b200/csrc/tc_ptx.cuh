@@ -117,10 +117,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool b_mn_m
   return (1u << 4) | (2u << 7) | (2u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
+// Round to the nearest tf32 (10 explicit mantissa bits), ties away from zero, on the integer ALU:
+// cvt.rna.tf32.f32 is a conversion-pipe instruction (a quarter of the FP32 issue rate) and the
+// transform warps round every element of every tile.
 __device__ __forceinline__ float round_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
 
 
