@@ -227,7 +227,18 @@ def run_ours(args):
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     if distributed:
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on STDOUT at communicator creation; keep stdout for the JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize(device)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.backends.cudnn.benchmark = True
     _native.lib()                                           # fail loudly if the extension is missing
