@@ -115,11 +115,11 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- model
-def build_model(layers, device, site_mode, seed=1):
+def build_model(layers, device, site_mode, seed=1, channels_last=False):
     from harness.resnet50_dwt import build_resnet50_dwt
     from harness.synth import synth_state_dict
     sd = {k: v.to(device) for k, v in synth_state_dict(seed=seed).items()}
-    model = build_resnet50_dwt(sd, layers, site_mode=site_mode).to(device)
+    model = build_resnet50_dwt(sd, layers, site_mode=site_mode, channels_last=channels_last).to(device)
     return model.train()
 
 
@@ -179,7 +179,8 @@ def run_reference(args):
 def workload_config(args, per_domain, site_mode):
     return {"workload": "ResNet-50-DWT synthetic Office-Home 224x224, train step = fwd + NLL + 0.1*MEC + bwd + SGD",
             "per_domain_batch": per_domain, "images_per_gpu": 3 * per_domain, "global_images": 3 * per_domain * args.gpus,
-            "group_size": 4, "site_mode": site_mode, "parallelism": f"dp{args.gpus}",
+            "group_size": 4, "site_mode": site_mode, "memory_format": getattr(args, "memory_format", "nchw"),
+            "parallelism": f"dp{args.gpus}",
             "l2": "no explicit flush: per-step working set (activations) is tens of GB >> 126 MB L2"}
 
 
@@ -246,7 +247,8 @@ def run_ours(args):
     if args.workload == "microbench":
         return run_microbench(args, device, rank)
 
-    model = build_model(dwt_b200, device, args.site_mode)
+    nhwc = args.memory_format == "nhwc"
+    model = build_model(dwt_b200, device, args.site_mode, channels_last=nhwc)
     net = model
     if distributed:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
@@ -255,6 +257,8 @@ def run_ours(args):
     mec = dwt_b200.MinEntropyConsensusLoss(NUM_CLASSES, device)
     B = args.per_domain
     host_images, host_labels = synth_batch(seed=100 + rank, per_domain=B)
+    if nhwc:
+        host_images = host_images.contiguous(memory_format=torch.channels_last)
     host_images, host_labels = host_images.pin_memory(), host_labels.pin_memory()
     images, labels = host_images.to(device), host_labels.to(device)
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
@@ -376,6 +380,8 @@ def main():
     ap.add_argument("--workload", choices=["resnet", "microbench"], default="resnet")
     ap.add_argument("--per-domain", type=int, default=64)
     ap.add_argument("--site-mode", choices=["fused", "modules"], default="fused")
+    ap.add_argument("--memory-format", choices=["nchw", "nhwc"], default="nhwc",
+                    help="activation layout of the GPU arm (nhwc = torch.channels_last end to end)")
     ap.add_argument("--cpu-per-domain", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--sites-out", default="", help="write the per-site kernel table (JSON) here")

@@ -18,6 +18,7 @@ MAX_DOMAINS = 4
 MAX_GROUP_SIZE = 64
 MODE_TRAIN, MODE_EVAL = 0, 1
 EPI_NONE, EPI_AFFINE, EPI_RELU = 0, 1, 2
+LAYOUT_NHWC = 0x100
 
 _c_float_p = ctypes.c_void_p
 _PtrArray = ctypes.c_void_p * MAX_DOMAINS
@@ -109,6 +110,14 @@ def lib() -> ctypes.CDLL:
                     raise NativeError("libdwt_b200.so ABI version mismatch; rebuild it")
                 _lib = handle
     return _lib
+
+
+def channels_last_supported(channels: int, group_size: int) -> bool:
+    """Mirror of cl_supports() in csrc/norm_cl.cu: group sizes 1/2/4 with C/4 a power of two."""
+    if group_size not in (1, 2, 4) or channels % 4:
+        return False
+    c4 = channels // 4
+    return c4 & (c4 - 1) == 0
 
 
 def check(rc: int) -> None:

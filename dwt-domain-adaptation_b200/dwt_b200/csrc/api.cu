@@ -114,6 +114,25 @@ int tc_apply_ctas(const dwt::Geom& g, int per_sm) {
   return n < 1 ? 1 : n;
 }
 
+// channels-last launch shaping: CTAs per (domain, column slab) for reductions (one wave) and elementwise kernels
+struct ClPlan { int nred, new_, S, gridy; };
+ClPlan cl_plan(const dwt::Geom& g, int slots_per_sm) {
+  const int C4 = g.C / 4, CW = C4 < 256 ? C4 : 256, rpi = 256 / CW, gridy = C4 / CW;
+  const long long rows = (long long)g.N * g.HW;
+  ClPlan p;
+  p.gridy = gridy;
+  long long by_work = rows / ((long long)rpi * 64);
+  if (by_work < 1) by_work = 1;
+  int cap = slots_per_sm * sm_count() / (gridy * g.D);
+  if (cap < 1) cap = 1;
+  p.nred = (int)(by_work < cap ? by_work : cap);
+  long long by_work_ew = rows / ((long long)rpi * 32);
+  if (by_work_ew < 1) by_work_ew = 1;
+  p.new_ = (int)(by_work_ew < 4LL * cap ? by_work_ew : 4LL * cap);
+  p.S = p.nred < 8 ? p.nred : 8;
+  return p;
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Launch shaping.  Every norm kernel is a single wave of long-lived CTAs: `target` CTAs in total
@@ -148,6 +167,7 @@ struct Workspace {
   float* dgb_part;    // [D*2*C]
   float* gram;        // [D*SB*(64*64+64)]  reduced moments of the tensor-core contraction
   float* shift;       // [D*SB*64]          pilot shift of every channel
+  float* red;         // [D*8*W]            channels-last path: split-reduced partial moments
   size_t bytes;
 };
 
@@ -176,7 +196,15 @@ Workspace carve(void* base, int64_t C, int GS, int D) {
     const size_t tc = ((size_t)2 * sm_count() + (size_t)((C + 63) / 64) * D) * (64 * 64 + 64);
     if (tc > partial_floats) partial_floats = tc;
   }
+  size_t red_floats = 1;
+  if (dwt::cl_supports((int)C, GS)) {                      // channels-last path: per-CTA rows of C/4-column vectors
+    const size_t W = (size_t)dwt::cl_bwd_width((int)C, GS);
+    const size_t cl = ((size_t)3 * sm_count() + 4 * D) * W;
+    if (cl > partial_floats) partial_floats = cl;
+    red_floats = (size_t)D * 8 * W;
+  }
   w.partial = reinterpret_cast<float*>(b + take(sizeof(float) * partial_floats));
+  w.red = reinterpret_cast<float*>(b + take(sizeof(float) * red_floats));
   w.save_cov = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * GS * GS));
   w.coef = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * G * dwt::coef_stride(GS)));
   w.dgb_part = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * 2 * C));
@@ -246,9 +274,14 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
                     float b, float momentum, float unbias, int update_running, float* const* rmean,
                     float* const* rcov, const float* gamma, const float* beta, int epi, float* save_mean,
                     float* save_w, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const bool nhwc = (mode & DWT_LAYOUT_NHWC) != 0;
+  mode &= 0xFF;
   Plan p;
   if (int rc = make_plan(p, K_STATS, K_APPLY, x, y, nullptr, N, C, HW, GS, D)) return rc;
   if (!x || !y || !save_mean || !save_w || !ws) return fail(DWT_E_INVALID, "null pointer argument");
+  if (nhwc && !dwt::cl_supports((int)C, GS))
+    return fail(DWT_E_UNSUPPORTED, "channels-last layout is built for group_size 1, 2, 4 with C/4 a power of two (C=%lld gs=%d)", (long long)C, GS);
+  if (nhwc && (((uintptr_t)x | (uintptr_t)y) % 16 != 0)) return fail(DWT_E_INVALID, "channels-last tensors must be 16-byte aligned");
   if (mode != DWT_MODE_TRAIN && mode != DWT_MODE_EVAL) return fail(DWT_E_INVALID, "bad mode %d", mode);
   if ((epi & DWT_EPI_RELU) && !(epi & DWT_EPI_AFFINE)) return fail(DWT_E_INVALID, "RELU epilogue needs AFFINE");
   if ((epi & DWT_EPI_AFFINE) && (!gamma || !beta)) return fail(DWT_E_INVALID, "AFFINE epilogue needs gamma and beta");
@@ -282,6 +315,28 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
   }
 
   const double E = 4.0 * (double)D * (double)N * (double)C * (double)HW;   // bytes of one activation tensor
+  if (nhwc) {
+    const ClPlan cp = cl_plan(p.gm, 3);
+    if (mode == DWT_MODE_TRAIN) {
+      {
+        Launch l("cl_stats", &p.gm, E, st);
+        dwt::cl_stats(x, p.gm, cp.nred, w.partial, w.shift, st);
+      }
+      if (int rc = check_launch("channels-last statistics kernel")) return rc;
+      Launch l("cl_fwd_finalize", &p.gm, 0.0, st);
+      dwt::cl_vec_reduce(w.partial, cp.nred, dwt::cl_fwd_width((int)C, GS), D, cp.S, w.red, st);
+      dwt::cl_fwd_finalize(w.red, cp.S, w.shift, p.gm, fin, st);
+    } else {
+      Launch l("eval_prep", &p.gm, 0.0, st);
+      dwt::small_eval_prep(p.gm, fin, st);
+    }
+    if (int rc = check_launch("channels-last finalize kernel")) return rc;
+    {
+      Launch l("cl_apply", &p.gm, 2 * E, st);
+      dwt::cl_apply(x, y, p.gm, cp.new_, epi, save_mean, save_w, gamma, beta, st);
+    }
+    return check_launch("channels-last apply kernel");
+  }
   const bool tc = !p.small && dwt::tc_supports(p.gm, p.vec) && ensure_tc() == 0;
   if (mode == DWT_MODE_TRAIN) {
     Launch l(p.small ? "small_stats" : (tc ? "tc_stats" : "tiled_stats"), &p.gm, E, st);
@@ -318,9 +373,14 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
                     int mode, float a, const float* save_mean, const float* save_w, const float* gamma,
                     const float* beta, int epi, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
                     cudaStream_t st) {
+  const bool nhwc = (mode & DWT_LAYOUT_NHWC) != 0;
+  mode &= 0xFF;
   Plan p;
   if (int rc = make_plan(p, K_BWD_REDUCE, K_BWD_APPLY, x, dout, dx, N, C, HW, GS, D)) return rc;
   if (!x || !dout || !dx || !save_mean || !save_w || !ws) return fail(DWT_E_INVALID, "null pointer argument");
+  if (nhwc && !dwt::cl_supports((int)C, GS))
+    return fail(DWT_E_UNSUPPORTED, "channels-last layout is built for group_size 1, 2, 4 with C/4 a power of two (C=%lld gs=%d)", (long long)C, GS);
+  if (nhwc && (((uintptr_t)x | (uintptr_t)dout | (uintptr_t)dx) % 16 != 0)) return fail(DWT_E_INVALID, "channels-last tensors must be 16-byte aligned");
   if (mode != DWT_MODE_TRAIN && mode != DWT_MODE_EVAL) return fail(DWT_E_INVALID, "bad mode %d", mode);
   if ((epi & DWT_EPI_RELU) && !(epi & DWT_EPI_AFFINE)) return fail(DWT_E_INVALID, "RELU epilogue needs AFFINE");
   if ((epi & DWT_EPI_AFFINE) && (!gamma || !beta)) return fail(DWT_E_INVALID, "AFFINE epilogue needs gamma and beta");
@@ -342,6 +402,28 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
 
   const bool need_reduce = (mode == DWT_MODE_TRAIN) || (fin.dgamma != nullptr);
   const double E = 4.0 * (double)D * (double)N * (double)C * (double)HW;
+  if (nhwc) {
+    const ClPlan cp = cl_plan(p.gm, 2);
+    if (need_reduce) {
+      {
+        Launch l("cl_bwd_reduce", &p.gm, 2 * E, st);
+        dwt::cl_bwd_reduce(x, dout, p.gm, cp.nred, epi, save_mean, save_w, gamma, beta, w.partial, st);
+      }
+      if (int rc = check_launch("channels-last backward reduction kernel")) return rc;
+      Launch l("cl_bwd_finalize", &p.gm, 0.0, st);
+      dwt::cl_vec_reduce(w.partial, cp.nred, dwt::cl_bwd_width((int)C, GS), D, cp.S, w.red, st);
+      dwt::cl_bwd_finalize(w.red, cp.S, p.gm, fin, st);
+    } else {
+      Launch l("bwd_prep", &p.gm, 0.0, st);
+      dwt::small_bwd_prep(p.gm, fin, st);
+    }
+    if (int rc = check_launch("channels-last backward finalize kernel")) return rc;
+    {
+      Launch l("cl_bwd_apply", &p.gm, 3 * E, st);
+      dwt::cl_bwd_apply(x, dout, dx, p.gm, cp.new_, epi, w.coef, save_mean, save_w, gamma, beta, st);
+    }
+    return check_launch("channels-last backward apply kernel");
+  }
   const bool tc = !p.small && dwt::tc_supports(p.gm, p.vec) && ensure_tc() == 0;
   if (need_reduce) {
     Launch l(p.small ? "small_bwd_reduce" : (tc ? "tc_bwd_reduce" : "tiled_bwd_reduce"), &p.gm, 2 * E, st);

@@ -1,0 +1,468 @@
+// Channels-last (NHWC) register-resident path for group sizes 1, 2, 4.
+//
+// cuDNN's tensor-core convolutions are NHWC kernels: fed NCHW fp32 tensors they bracket every
+// convolution with nchwToNhwc / nhwcToNchw copies (12.8 % of the ResNet-50-DWT step,
+// profiles/launches_r01a_summary.md).  Running the whole model channels-last removes those copies,
+// provided the normalisation layers in between read and write NHWC natively -- this file.
+//
+// Layout: x[(n*HW + p)*C + c].  One float4 = 4 consecutive channels of one pixel = one whitening
+// group (gs = 4), two groups (gs = 2) or four batch-norm channels (gs = 1).  A thread owns one float4
+// COLUMN q (channels 4q..4q+3) and walks down the rows (pixels); a warp therefore reads 512
+// contiguous bytes per step, and a thread's accumulators always belong to the same channels.
+// A CTA covers CW = min(C/4, 256) columns x a contiguous range of rows; 256/CW threads share a column
+// and are summed in shared memory.  Per-CTA partial moments go to global memory, a small
+// many-CTA kernel adds them in fixed order, and a one-thread-per-group kernel does the dense algebra
+// (small_algebra.cuh) for all domains in order -- so the running-statistic EMA needs no atomics.
+//
+//   cl_stats -> vec_reduce -> cl_fwd_finalize -> cl_apply          (forward, 12 B/element)
+//   cl_bwd_reduce -> vec_reduce -> cl_bwd_finalize -> cl_bwd_apply (backward, 20 B/element)
+//
+// Reference semantics: utils/whitening.py:37-61, utils/batch_norm.py:54-69 (/root/reference).
+#include "dwt_common.cuh"
+#include "norm_launch.h"
+#include "small_algebra.cuh"
+
+namespace dwt {
+namespace {
+
+constexpr int kT = 256;
+
+template <int GS> struct ClShape {
+  static constexpr int NSUB = 4 / GS;                       // problems per float4 column
+  static constexpr int NM = GS * (GS + 1) / 2;
+  static constexpr int FWD1 = GS + NM;                      // forward accumulators per problem
+  static constexpr int BWD1 = GS * GS + GS;                 // backward accumulators per problem
+  static constexpr int FWD = NSUB * FWD1;
+  static constexpr int BWD = NSUB * BWD1;
+};
+
+// Thread placement inside the CTA.
+struct ClThread {
+  int C4, CW, rpi, col, rsub, q;
+  unsigned r0, r1;            // row range of this CTA inside the domain
+  __device__ __forceinline__ ClThread(const Geom& gm) {
+    C4 = gm.C >> 2;
+    CW = C4 < kT ? C4 : kT;
+    rpi = kT / CW;
+    col = threadIdx.x % CW;
+    rsub = threadIdx.x / CW;
+    q = blockIdx.y * CW + col;
+    const unsigned rows = (unsigned)gm.N * gm.HW;
+    r0 = (unsigned)((unsigned long long)rows * blockIdx.x / gridDim.x);
+    r1 = (unsigned)((unsigned long long)rows * (blockIdx.x + 1) / gridDim.x);
+  }
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Sum the per-thread accumulators of the rpi threads that share a column; thread rsub == 0 of every column
+// then holds the CTA total.  sRed must hold kT * NACC floats.
+template <int NACC>
+__device__ __forceinline__ void column_reduce(const ClThread& t, float (&acc)[NACC], float* sRed) {
+  if (t.rpi == 1) return;
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) sRed[i * kT + threadIdx.x] = acc[i];
+  __syncthreads();
+  if (t.rsub == 0) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+      float s = acc[i];
+      for (int r = 1; r < t.rpi; ++r) s += sRed[i * kT + r * t.CW + t.col];
+      acc[i] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward statistics: partial[d][cta][q][FWD] ; CTA (0, y, d) also publishes the pilot shift
+// ------------------------------------------------------------------------------------------
+template <int GS>
+__global__ void __launch_bounds__(kT, 3) cl_stats_kernel(const float* __restrict__ x, const Geom gm,
+                                                         float* __restrict__ partial, float* __restrict__ shift) {
+  using S = ClShape<GS>;
+  constexpr int UNROLL = 8;
+  __shared__ float sRed[kT * S::FWD];
+  const ClThread t(gm);
+  const int d = blockIdx.z;
+  const unsigned rows = (unsigned)gm.N * gm.HW;
+  const float* xd = x + (size_t)d * rows * gm.C + 4 * t.q;
+  // pilot shift: mean of the first <= 8 rows of the domain, per channel (every thread of a column agrees)
+  float K[4] = {0.f, 0.f, 0.f, 0.f};
+  {
+    const unsigned np = rows < 8 ? rows : 8;
+    for (unsigned r = 0; r < np; ++r) {
+      const float4 v = ldg4(xd + (size_t)r * gm.C);
+      K[0] += v.x; K[1] += v.y; K[2] += v.z; K[3] += v.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) K[c] /= (float)np;
+    if (blockIdx.x == 0 && t.rsub == 0) *reinterpret_cast<float4*>(shift + (size_t)d * gm.C + 4 * t.q) = make_float4(K[0], K[1], K[2], K[3]);
+  }
+  float acc[S::FWD];
+#pragma unroll
+  for (int i = 0; i < S::FWD; ++i) acc[i] = 0.f;
+  for (unsigned r = t.r0 + t.rsub; r < t.r1; r += t.rpi * UNROLL) {
+    float4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const unsigned rr = r + u * t.rpi;
+      v[u] = rr < t.r1 ? ldg4(xd + (size_t)rr * gm.C) : make_float4(K[0], K[1], K[2], K[3]);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const float e[4] = {v[u].x - K[0], v[u].y - K[1], v[u].z - K[2], v[u].w - K[3]};
+#pragma unroll
+      for (int s = 0; s < S::NSUB; ++s) {
+#pragma unroll
+        for (int c = 0; c < GS; ++c) {
+          acc[s * S::FWD1 + c] += e[s * GS + c];
+#pragma unroll
+          for (int j = 0; j <= c; ++j)
+            acc[s * S::FWD1 + GS + c * (c + 1) / 2 + j] = fmaf(e[s * GS + c], e[s * GS + j], acc[s * S::FWD1 + GS + c * (c + 1) / 2 + j]);
+        }
+      }
+    }
+  }
+  column_reduce<S::FWD>(t, acc, sRed);
+  if (t.rsub == 0) {
+    float* dst = partial + (((size_t)d * gridDim.x + blockIdx.x) * t.C4 + t.q) * S::FWD;
+#pragma unroll
+    for (int i = 0; i < S::FWD; ++i) dst[i] = acc[i];
+  }
+}
+
+// out[d][s][e] = sum over the rows of split s of partial[d][row][e]  (fixed order).
+// grid (ceil(W/64), D, S), 256 threads = 4 row-quarters x 64 elements.
+__global__ void __launch_bounds__(256) vec_reduce_kernel(const float* __restrict__ partial, int nrows, int W,
+                                                         float* __restrict__ out) {
+  __shared__ float sQ[4][64];
+  const int l = threadIdx.x & 63, qt = threadIdx.x >> 6, S = gridDim.z;
+  const int e = blockIdx.x * 64 + l, d = blockIdx.y, s = blockIdx.z;
+  const int a0 = (int)((long long)nrows * s / S), a1 = (int)((long long)nrows * (s + 1) / S);
+  const int c0 = a0 + ((a1 - a0) * qt) / 4, c1 = a0 + ((a1 - a0) * (qt + 1)) / 4;
+  const float* base = partial + (size_t)d * nrows * W;
+  float acc = 0.f;
+  if (e < W) {
+    int c = c0;
+    for (; c + 4 <= c1; c += 4) {
+      const float v0 = __ldcg(base + (size_t)(c + 0) * W + e), v1 = __ldcg(base + (size_t)(c + 1) * W + e);
+      const float v2 = __ldcg(base + (size_t)(c + 2) * W + e), v3 = __ldcg(base + (size_t)(c + 3) * W + e);
+      acc = (((acc + v0) + v1) + v2) + v3;
+    }
+    for (; c < c1; ++c) acc += __ldcg(base + (size_t)c * W + e);
+  }
+  sQ[qt][l] = acc;
+  __syncthreads();
+  if (qt == 0 && e < W) out[((size_t)d * S + s) * W + e] = ((sQ[0][l] + sQ[1][l]) + sQ[2][l]) + sQ[3][l];
+}
+
+// index of accumulator a of group g inside a W-vector
+template <int GS, int PER>
+__device__ __forceinline__ int acc_index(int g, int a) {
+  constexpr int NSUB = 4 / GS;
+  return (g / NSUB) * (NSUB * PER) + (g % NSUB) * PER + a;
+}
+
+// one thread per group, all domains in order
+template <int GS>
+__global__ void __launch_bounds__(128) cl_fwd_finalize_kernel(const float* __restrict__ red, int S, const float* __restrict__ shift,
+                                                              const Geom gm, const FwdFin fin) {
+  using SH = ClShape<GS>;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= gm.G) return;
+  const int W = (gm.C >> 2) * SH::FWD;
+  const float invM = 1.f / gm.M;
+  for (int d = 0; d < gm.D; ++d) {
+    float a[SH::FWD1];
+#pragma unroll
+    for (int i = 0; i < SH::FWD1; ++i) {
+      float s = 0.f;
+      for (int k = 0; k < S; ++k) s += red[((size_t)d * S + k) * W + acc_index<GS, SH::FWD1>(g, i)];
+      a[i] = s;
+    }
+    float mean[GS], cov[GS][GS];
+#pragma unroll
+    for (int i = 0; i < GS; ++i) mean[i] = shift[(size_t)d * gm.C + g * GS + i] + a[i] * invM;
+#pragma unroll
+    for (int i = 0; i < GS; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        const float c = a[GS + i * (i + 1) / 2 + j] * invM - (a[i] * invM) * (a[j] * invM);
+        cov[i][j] = c; cov[j][i] = c;
+      }
+    factor_thread<GS>(gm, fin, d, g, mean, cov, true);
+    ema_thread<GS>(gm, fin, d, g, mean, cov);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// apply
+// ------------------------------------------------------------------------------------------
+template <int GS, int EPI>
+__global__ void __launch_bounds__(kT, 3) cl_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const Geom gm,
+                                                         const float* __restrict__ save_mean, const float* __restrict__ save_w,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta) {
+  using S = ClShape<GS>;
+  constexpr int UNROLL = 8;
+  const ClThread t(gm);
+  const int d = blockIdx.z;
+  float Wp[S::NSUB][S::NM], bp[S::NSUB][GS];
+#pragma unroll
+  for (int s = 0; s < S::NSUB; ++s) {
+    const int g = t.q * S::NSUB + s;
+    load_forward_map<GS, EPI>(save_w + ((size_t)d * gm.G + g) * GS * GS, save_mean + (size_t)d * gm.C + g * GS,
+                              gamma + g * GS, beta + g * GS, Wp[s], bp[s]);
+  }
+  const size_t base = (size_t)d * gm.N * gm.HW * gm.C + 4 * t.q;
+  const float* xd = x + base;
+  float* yd = y + base;
+  for (unsigned r = t.r0 + t.rsub; r < t.r1; r += t.rpi * UNROLL) {
+    float4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const unsigned rr = r + u * t.rpi;
+      if (rr < t.r1) v[u] = ldg4(xd + (size_t)rr * gm.C);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const unsigned rr = r + u * t.rpi;
+      if (rr < t.r1) {
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        float o[4];
+#pragma unroll
+        for (int s = 0; s < S::NSUB; ++s) {
+          float xi[GS], oi[GS];
+#pragma unroll
+          for (int c = 0; c < GS; ++c) xi[c] = e[s * GS + c];
+          apply_group<GS>(Wp[s], bp[s], xi, oi);
+#pragma unroll
+          for (int c = 0; c < GS; ++c) o[s * GS + c] = (EPI & DWT_EPI_RELU) ? fmaxf(oi[c], 0.f) : oi[c];
+        }
+        *reinterpret_cast<float4*>(yd + (size_t)rr * gm.C) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward reduce: partial[d][cta][q][BWD]  (per problem: R row-major, then sdz)
+// ------------------------------------------------------------------------------------------
+template <int GS, int EPI>
+__global__ void __launch_bounds__(kT, 2) cl_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dout,
+                                                              const Geom gm, const float* __restrict__ save_mean,
+                                                              const float* __restrict__ save_w, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float* __restrict__ partial) {
+  using S = ClShape<GS>;
+  constexpr int UNROLL = 4;
+  constexpr bool RELU = (EPI & DWT_EPI_RELU) != 0;
+  __shared__ float sRed[kT * S::BWD];
+  const ClThread t(gm);
+  const int d = blockIdx.z;
+  float Wp[S::NSUB][S::NM], bp[S::NSUB][GS], mu[4];
+#pragma unroll
+  for (int s = 0; s < S::NSUB; ++s) {
+    const int g = t.q * S::NSUB + s;
+    if constexpr (RELU)
+      load_forward_map<GS, EPI>(save_w + ((size_t)d * gm.G + g) * GS * GS, save_mean + (size_t)d * gm.C + g * GS,
+                                gamma + g * GS, beta + g * GS, Wp[s], bp[s]);
+  }
+  {
+    const float4 m4 = ldg4(save_mean + (size_t)d * gm.C + 4 * t.q);
+    mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w;
+  }
+  float acc[S::BWD];
+#pragma unroll
+  for (int i = 0; i < S::BWD; ++i) acc[i] = 0.f;
+  const size_t base = (size_t)d * gm.N * gm.HW * gm.C + 4 * t.q;
+  const float* xd = x + base;
+  const float* gd = dout + base;
+  for (unsigned r = t.r0 + t.rsub; r < t.r1; r += t.rpi * UNROLL) {
+    float4 v[UNROLL], q[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const unsigned rr = r + u * t.rpi;
+      if (rr < t.r1) { v[u] = ldg4(xd + (size_t)rr * gm.C); q[u] = ldg4(gd + (size_t)rr * gm.C); }
+      else { v[u] = make_float4(mu[0], mu[1], mu[2], mu[3]); q[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, ge[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+      for (int s = 0; s < S::NSUB; ++s) {
+        float xi[GS], dz[GS];
+#pragma unroll
+        for (int c = 0; c < GS; ++c) { xi[c] = e[s * GS + c]; dz[c] = ge[s * GS + c]; }
+        if constexpr (RELU) {
+          float oi[GS];
+          apply_group<GS>(Wp[s], bp[s], xi, oi);
+#pragma unroll
+          for (int c = 0; c < GS; ++c) dz[c] = oi[c] > 0.f ? dz[c] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < GS; ++i) {
+          acc[s * S::BWD1 + GS * GS + i] += dz[i];
+#pragma unroll
+          for (int j = 0; j < GS; ++j) acc[s * S::BWD1 + i * GS + j] = fmaf(dz[i], xi[j] - mu[s * GS + j], acc[s * S::BWD1 + i * GS + j]);
+        }
+      }
+    }
+  }
+  column_reduce<S::BWD>(t, acc, sRed);
+  if (t.rsub == 0) {
+    float* dst = partial + (((size_t)d * gridDim.x + blockIdx.x) * t.C4 + t.q) * S::BWD;
+#pragma unroll
+    for (int i = 0; i < S::BWD; ++i) dst[i] = acc[i];
+  }
+}
+
+template <int GS>
+__global__ void __launch_bounds__(128) cl_bwd_finalize_kernel(const float* __restrict__ red, int S, const Geom gm, const BwdFin fin) {
+  using SH = ClShape<GS>;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= gm.G) return;
+  const int W = (gm.C >> 2) * SH::BWD;
+  for (int d = 0; d < gm.D; ++d) {
+    float R[GS][GS], sdz[GS];
+#pragma unroll
+    for (int i = 0; i < SH::BWD1; ++i) {
+      float s = 0.f;
+      if (red != nullptr)
+        for (int k = 0; k < S; ++k) s += red[((size_t)d * S + k) * W + acc_index<GS, SH::BWD1>(g, i)];
+      if (i < GS * GS) R[i / GS][i % GS] = s; else sdz[i - GS * GS] = s;
+    }
+    bwd_finalize_thread<GS>(gm, fin, d, g, R, sdz);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward apply
+// ------------------------------------------------------------------------------------------
+template <int GS, int EPI>
+__global__ void __launch_bounds__(kT, 2) cl_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dout,
+                                                             float* __restrict__ dx, const Geom gm, const float* __restrict__ coef,
+                                                             const float* __restrict__ save_mean, const float* __restrict__ save_w,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta) {
+  using S = ClShape<GS>;
+  constexpr int UNROLL = 4;
+  constexpr bool RELU = (EPI & DWT_EPI_RELU) != 0;
+  const ClThread t(gm);
+  const int d = blockIdx.z;
+  float Wp[S::NSUB][S::NM], bp[S::NSUB][GS], A1[S::NSUB][S::NM], Bm[S::NSUB][S::NM], cv[S::NSUB][GS];
+#pragma unroll
+  for (int s = 0; s < S::NSUB; ++s) {
+    const int g = t.q * S::NSUB + s;
+    if constexpr (RELU)
+      load_forward_map<GS, EPI>(save_w + ((size_t)d * gm.G + g) * GS * GS, save_mean + (size_t)d * gm.C + g * GS,
+                                gamma + g * GS, beta + g * GS, Wp[s], bp[s]);
+    const float* cf = coef + ((size_t)d * gm.G + g) * coef_stride(GS);
+#pragma unroll
+    for (int i = 0; i < GS; ++i) {
+      cv[s][i] = __ldg(cf + 2 * GS * GS + i);
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        A1[s][i * (i + 1) / 2 + j] = __ldg(cf + j * GS + i);
+        Bm[s][i * (i + 1) / 2 + j] = __ldg(cf + GS * GS + i * GS + j);
+      }
+    }
+  }
+  const size_t base = (size_t)d * gm.N * gm.HW * gm.C + 4 * t.q;
+  const float* xd = x + base;
+  const float* gd = dout + base;
+  float* od = dx + base;
+  for (unsigned r = t.r0 + t.rsub; r < t.r1; r += t.rpi * UNROLL) {
+    float4 v[UNROLL], q[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const unsigned rr = r + u * t.rpi;
+      if (rr < t.r1) { v[u] = ldg4(xd + (size_t)rr * gm.C); q[u] = ldg4(gd + (size_t)rr * gm.C); }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const unsigned rr = r + u * t.rpi;
+      if (rr < t.r1) {
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, ge[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+        float o[4];
+#pragma unroll
+        for (int s = 0; s < S::NSUB; ++s) {
+          float xi[GS], dz[GS];
+#pragma unroll
+          for (int c = 0; c < GS; ++c) { xi[c] = e[s * GS + c]; dz[c] = ge[s * GS + c]; }
+          if constexpr (RELU) {
+            float oi[GS];
+            apply_group<GS>(Wp[s], bp[s], xi, oi);
+#pragma unroll
+            for (int c = 0; c < GS; ++c) dz[c] = oi[c] > 0.f ? dz[c] : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < GS; ++i) {
+            float a = cv[s][i];
+#pragma unroll
+            for (int j = i; j < GS; ++j) a = fmaf(A1[s][j * (j + 1) / 2 + i], dz[j], a);
+#pragma unroll
+            for (int j = 0; j < GS; ++j) {
+              const int hi = i > j ? i : j, lo = i > j ? j : i;
+              a = fmaf(Bm[s][hi * (hi + 1) / 2 + lo], xi[j], a);
+            }
+            o[s * GS + i] = a;
+          }
+        }
+        *reinterpret_cast<float4*>(od + (size_t)rr * gm.C) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+#define CL_GS(GS_, ...)                                  \
+  switch (GS_) {                                         \
+    case 1: { constexpr int kGS = 1; __VA_ARGS__; break; } \
+    case 2: { constexpr int kGS = 2; __VA_ARGS__; break; } \
+    case 4: { constexpr int kGS = 4; __VA_ARGS__; break; } \
+    default: break;                                      \
+  }
+#define CL_EPI(E_, ...)                                                   \
+  if ((E_) == 3) { constexpr int kEPI = 3; __VA_ARGS__; }                 \
+  else if ((E_) == 1) { constexpr int kEPI = 1; __VA_ARGS__; }            \
+  else { constexpr int kEPI = 0; __VA_ARGS__; }
+
+inline dim3 cl_grid(const Geom& gm, int nctas) {
+  const int C4 = gm.C / 4, CW = C4 < kT ? C4 : kT;
+  return dim3(nctas, C4 / CW, gm.D);
+}
+
+}  // namespace
+
+// C/4 must be a power of two (every thread keeps one float4 column for the whole kernel)
+bool cl_supports(int C, int GS) {
+  if (!(GS == 1 || GS == 2 || GS == 4) || C % 4 != 0) return false;
+  const int c4 = C / 4;
+  return (c4 & (c4 - 1)) == 0 && c4 <= 16384;
+}
+int cl_fwd_width(int C, int GS) { return (C / 4) * (4 / GS) * (GS + GS * (GS + 1) / 2); }
+int cl_bwd_width(int C, int GS) { return (C / 4) * (4 / GS) * (GS * GS + GS); }
+
+void cl_stats(const float* x, const Geom& gm, int nctas, float* partial, float* shift, cudaStream_t st) {
+  CL_GS(gm.GS, (cl_stats_kernel<kGS><<<cl_grid(gm, nctas), kT, 0, st>>>(x, gm, partial, shift)));
+}
+void cl_vec_reduce(const float* partial, int nrows, int W, int D, int S, float* out, cudaStream_t st) {
+  vec_reduce_kernel<<<dim3((W + 63) / 64, D, S), 256, 0, st>>>(partial, nrows, W, out);
+}
+void cl_fwd_finalize(const float* red, int S, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st) {
+  CL_GS(gm.GS, (cl_fwd_finalize_kernel<kGS><<<(gm.G + 127) / 128, 128, 0, st>>>(red, S, shift, gm, fin)));
+}
+void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
+              const float* gamma, const float* beta, cudaStream_t st) {
+  CL_GS(gm.GS, CL_EPI(epi, (cl_apply_kernel<kGS, kEPI><<<cl_grid(gm, nctas), kT, 0, st>>>(x, y, gm, mean, w, gamma, beta))));
+}
+void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
+                   const float* gamma, const float* beta, float* partial, cudaStream_t st) {
+  CL_GS(gm.GS, CL_EPI(epi, (cl_bwd_reduce_kernel<kGS, kEPI><<<cl_grid(gm, nctas), kT, 0, st>>>(x, dout, gm, mean, w, gamma, beta, partial))));
+}
+void cl_bwd_finalize(const float* red, int S, const Geom& gm, const BwdFin& fin, cudaStream_t st) {
+  CL_GS(gm.GS, (cl_bwd_finalize_kernel<kGS><<<(gm.G + 127) / 128, 128, 0, st>>>(red, S, gm, fin)));
+}
+void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, int epi, const float* coef,
+                  const float* mean, const float* w, const float* gamma, const float* beta, cudaStream_t st) {
+  CL_GS(gm.GS, CL_EPI(epi, (cl_bwd_apply_kernel<kGS, kEPI><<<cl_grid(gm, nctas), kT, 0, st>>>(x, dout, dx, gm, coef, mean, w, gamma, beta))));
+}
+
+}  // namespace dwt

@@ -53,6 +53,21 @@ int tc_apply(const float* x, float* y, const Geom& gm, int nctas, const float* s
 int tc_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, const float* coef,
                  const float* save_mean, const float* dybar, cudaStream_t st);
 
+// channels-last (NHWC) register-resident path, GS in {1,2,4}, C/4 a power of two  (norm_cl.cu)
+bool cl_supports(int C, int GS);
+int cl_fwd_width(int C, int GS);
+int cl_bwd_width(int C, int GS);
+void cl_stats(const float* x, const Geom& gm, int nctas, float* partial, float* shift, cudaStream_t st);
+void cl_vec_reduce(const float* partial, int nrows, int W, int D, int S, float* out, cudaStream_t st);
+void cl_fwd_finalize(const float* red, int S, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st);
+void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
+              const float* gamma, const float* beta, cudaStream_t st);
+void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
+                   const float* gamma, const float* beta, float* partial, cudaStream_t st);
+void cl_bwd_finalize(const float* red, int S, const Geom& gm, const BwdFin& fin, cudaStream_t st);
+void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, int epi, const float* coef,
+                  const float* mean, const float* w, const float* gamma, const float* beta, cudaStream_t st);
+
 // MEC loss (mec.cu)
 void mec_launch(const float* x, const float* y, int N, int K, float* loss, float* gx, float* gy, cudaStream_t st);
 

@@ -11,15 +11,20 @@ import torch
 from . import _native as nv
 
 
-def _as_nchw(x: torch.Tensor):
-    """[N, C, *spatial] -> contiguous tensor, (N, C, HW)."""
-    if not x.is_contiguous():
-        x = x.contiguous()
+def _dense(x: torch.Tensor, group_size: int):
+    """[N, C, *spatial] -> (dense tensor, N, C, HW, channels_last?).
+
+    A 4-D tensor that is already dense in torch.channels_last order is used as it is (NHWC kernels) when
+    the geometry has a channels-last build; anything else is made NCHW-contiguous."""
     n, c = x.shape[0], x.shape[1]
     hw = 1
     for s in x.shape[2:]:
         hw *= s
-    return x, n, c, hw
+    nhwc = (x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+            and nv.channels_last_supported(c, group_size))
+    if not nhwc and not x.is_contiguous():
+        x = x.contiguous()
+    return x, n, c, hw, nhwc
 
 
 class _NormFunction(torch.autograd.Function):
@@ -33,7 +38,9 @@ class _NormFunction(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, kind, group_size, n_domains, mode, eps, momentum, update_running,
                 running, relu):
         lib = nv.lib()
-        x, n_all, c, hw = _as_nchw(x)
+        gs = group_size if kind == "whiten" else 1
+        x, n_all, c, hw, nhwc = _dense(x, gs)
+        layout = nv.LAYOUT_NHWC if nhwc else 0
         if n_all % n_domains != 0:
             raise ValueError(f"batch of {n_all} does not split into {n_domains} domains")
         n = n_all // n_domains
@@ -44,8 +51,7 @@ class _NormFunction(torch.autograd.Function):
             gamma_c, beta_c = gamma.detach().reshape(-1).contiguous(), beta.detach().reshape(-1).contiguous()
         else:
             gamma_c = beta_c = None
-        gs = group_size if kind == "whiten" else 1
-        y = torch.empty_like(x)
+        y = torch.empty_like(x)                      # keeps x's memory format
         save_mean = torch.empty(n_domains, c, dtype=torch.float32, device=dev)
         save_w = torch.empty(n_domains, c // gs, gs, gs, dtype=torch.float32, device=dev)
         ws = nv.workspace(dev, n, c, hw, gs, n_domains)
@@ -54,16 +60,16 @@ class _NormFunction(torch.autograd.Function):
         rv = nv.ptr_array([p[1] for p in running]) if need_running else None
         with torch.cuda.device(dev):
             if kind == "whiten":
-                rc = lib.dwt_whiten_fwd(nv.ptr(x), nv.ptr(y), n, c, hw, gs, n_domains, mode, eps, momentum,
+                rc = lib.dwt_whiten_fwd(nv.ptr(x), nv.ptr(y), n, c, hw, gs, n_domains, mode | layout, eps, momentum,
                                         int(update_running), rm, rv, nv.ptr(gamma_c), nv.ptr(beta_c), epi,
                                         nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
             else:
-                rc = lib.dwt_bn_fwd(nv.ptr(x), nv.ptr(y), n, c, hw, n_domains, mode, eps, momentum,
+                rc = lib.dwt_bn_fwd(nv.ptr(x), nv.ptr(y), n, c, hw, n_domains, mode | layout, eps, momentum,
                                     int(update_running), rm, rv, nv.ptr(gamma_c), nv.ptr(beta_c), epi,
                                     nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
         nv.check(rc)
         ctx.save_for_backward(x, save_mean, save_w, gamma_c, beta_c)
-        ctx.cfg = (kind, gs, n_domains, mode, eps, epi, n, c, hw, None if gamma is None else gamma.shape)
+        ctx.cfg = (kind, gs, n_domains, mode | layout, eps, epi, n, c, hw, None if gamma is None else gamma.shape)
         return y
 
     @staticmethod
@@ -71,7 +77,7 @@ class _NormFunction(torch.autograd.Function):
         lib = nv.lib()
         x, save_mean, save_w, gamma_c, beta_c = ctx.saved_tensors
         kind, gs, n_domains, mode, eps, epi, n, c, hw, gshape = ctx.cfg
-        dout = dout.contiguous()
+        dout = dout.contiguous(memory_format=torch.channels_last) if (mode & nv.LAYOUT_NHWC) else dout.contiguous()
         dev = nv.require_cuda(dout)
         dx = torch.empty_like(x)
         want_affine = gamma_c is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])

@@ -161,9 +161,13 @@ class ResNet50DWT(_SiteOwner):
         return self.fc_out(torch.flatten(self.avgpool(x), 1))
 
 
-def build_resnet50_dwt(state_dict, layers, site_mode="modules", num_classes=65):
+def build_resnet50_dwt(state_dict, layers, site_mode="modules", num_classes=65, channels_last=False):
     """state_dict uses the reference checkpoint's key names *without* the 7-char
-    ``module.`` prefix (resnet50_dwt_mec_officehome.py:370-376)."""
+    ``module.`` prefix (resnet50_dwt_mec_officehome.py:370-376).  channels_last=True converts the
+    convolution weights to torch.channels_last so that, fed channels-last images, every activation
+    stays NHWC (no cuDNN NCHW<->NHWC copies); results are identical, only strides change."""
     model = ResNet50DWT(layers, state_dict, num_classes=num_classes, site_mode=site_mode)
     model.load_state_dict(state_dict, strict=False)
+    if channels_last:
+        model = model.to(memory_format=torch.channels_last)
     return model

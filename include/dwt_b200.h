@@ -50,6 +50,12 @@ extern "C" {
 #define DWT_MODE_TRAIN 0 /* batch statistics (training, or track_running_stats=False) */
 #define DWT_MODE_EVAL 1  /* running statistics                                        */
 
+/* memory layout of the activation tensors, OR-ed into `mode`:
+ * default = [n_domains*N, C, HW] (NCHW); DWT_LAYOUT_NHWC = [n_domains*N, HW, C] (torch.channels_last), built for
+ * group sizes 1, 2, 4 with C/4 a power of two (the layout cuDNN's tensor-core convolutions want: a
+ * channels-last model needs no NCHW<->NHWC copies around its convolutions). */
+#define DWT_LAYOUT_NHWC 0x100
+
 /* epilogue flags */
 #define DWT_EPI_NONE 0
 #define DWT_EPI_AFFINE 1 /* out = y * gamma[c] + beta[c]        */

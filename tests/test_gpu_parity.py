@@ -396,3 +396,102 @@ def test_fused_triple_buffer_aliasing_classes(layout, dev):
         DomainTripleNorm("whiten", c, gs)(t(x, dev), mods, g_t, b_t, relu=False)
     for o in set(owner):
         assert rel_err(n(tb[o][0]).reshape(-1), bufs[o][0]) < TOL_STAT and rel_err(n(tb[o][1]), bufs[o][1]) < TOL_STAT
+
+
+# --------------------------------------------------------------------------- channels-last (NHWC) kernels
+@pytest.mark.parametrize("kind,c,hw,gs", [("whiten", 64, 28, 4), ("whiten", 256, 14, 4), ("whiten", 16, 10, 4),
+                                           ("whiten", 32, 9, 2), ("bn", 128, 14, 1), ("bn", 2048, 7, 1), ("bn", 8, 5, 1)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_channels_last_site_matches_oracle(kind, c, hw, gs, relu, dev):
+    """The NHWC kernels (torch.channels_last tensors) against the same oracle as the NCHW ones: fused domain
+    triple on aliased buffers, forward, backward, dgamma/dbeta, EMA."""
+    import batch_norm
+    import whitening
+    from dwt_b200 import DomainTripleNorm
+    rng = np.random.default_rng(31)
+    nper = 6
+    x = np.concatenate([_correlated(rng, nper, c, hw, hw, offset=o) for o in (0.5, -1.0, 2.0)])
+    dout = rng.standard_normal(x.shape)
+    gamma, beta = 0.5 + rng.random(c), 0.3 * rng.standard_normal(c)
+    if kind == "whiten":
+        rm = 0.1 * rng.standard_normal(c)
+        a = rng.standard_normal((c // gs, gs, gs))
+        rv = a @ a.transpose(0, 2, 1) / gs + 0.5 * np.eye(gs)
+    else:
+        rm, rv = 0.1 * rng.standard_normal(c), 0.5 + rng.random(c)
+    outs, dxs = [], []
+    dgamma, dbeta = np.zeros(c), np.zeros(c)
+    rm_o, rv_o = rm, rv
+    for d in range(3):
+        xd, dd = x[d * nper:(d + 1) * nper], dout[d * nper:(d + 1) * nper]
+        if kind == "whiten":
+            y, mean, w, rm_o, rv_o, _ = O.whiten_forward(xd, gs, running_mean=rm_o, running_cov=rv_o)
+        else:
+            y, mean, inv, rm_o, rv_o = O.bn_forward(xd, rm_o, rv_o)
+        pre = O.scale_shift_relu(y, gamma, beta, False)
+        dz = dd * (pre > 0) if relu else dd
+        dgamma += (dz * y).sum(axis=(0, 2, 3)); dbeta += dz.sum(axis=(0, 2, 3))
+        dyd = dz * gamma.reshape(1, c, 1, 1)
+        dxs.append(O.whiten_backward(xd, dyd, mean, w) if kind == "whiten" else O.bn_backward(xd, dyd, mean, inv)[0])
+        outs.append(np.maximum(pre, 0) if relu else pre)
+    rm_t = t(rm.reshape(1, c, 1, 1) if kind == "whiten" else rm, dev)
+    rv_t = t(rv, dev)
+    if kind == "whiten":
+        mods = [whitening.WTransform2d(c, gs, running_m=rm_t, running_var=rv_t).train() for _ in range(3)]
+    else:
+        mods = [batch_norm.BatchNorm2d(c, rm_t, rv_t, affine=False).train() for _ in range(3)]
+    g_t = t(gamma.reshape(c, 1, 1), dev).requires_grad_(True)
+    b_t = t(beta.reshape(c, 1, 1), dev).requires_grad_(True)
+    xt = t(x, dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    out = DomainTripleNorm(kind, c, gs)(xt, mods, g_t, b_t, relu=relu)
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    out.backward(t(dout, dev).contiguous(memory_format=torch.channels_last))
+    assert xt.grad.is_contiguous(memory_format=torch.channels_last)
+    tol = TOL if kind == "whiten" else TOL_STAT
+    assert rel_err(n(out), np.concatenate(outs)) < tol and rel_err(n(xt.grad), np.concatenate(dxs)) < tol
+    assert rel_err(n(g_t.grad).reshape(-1), dgamma) < tol and rel_err(n(b_t.grad).reshape(-1), dbeta) < tol
+    assert rel_err(n(rm_t).reshape(-1), rm_o) < TOL_STAT and rel_err(n(rv_t), rv_o) < TOL_STAT
+
+
+def test_channels_last_module_paths(dev):
+    """Single-domain modules on channels-last input: train, no-grad train, eval (+ backward), and a channel count
+    without a channels-last build (C/4 not a power of two) silently takes the NCHW kernels."""
+    import whitening
+    rng = np.random.default_rng(41)
+    for c, gs in [(64, 4), (48, 4)]:
+        x = _correlated(rng, 5, c, 12, 12)
+        dy = rng.standard_normal(x.shape)
+        y_o, mean_o, w_o, rm1, rv1, _ = O.whiten_forward(x, gs, running_mean=np.zeros(c), running_cov=np.ones((c // gs, gs, gs)))
+        m = whitening.WTransform2d(c, gs).to(dev).train()
+        xt = t(x, dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        y = m(xt)
+        (dx,) = torch.autograd.grad(y, xt, t(dy, dev))
+        assert rel_err(n(y), y_o) < TOL and rel_err(n(dx), O.whiten_backward(x, dy, mean_o, w_o)) < TOL
+        assert rel_err(n(m.running_variance), rv1) < TOL_STAT
+        m.eval()
+        ye, _, we, *_ = O.whiten_forward(x, gs, running_mean=rm1, running_cov=rv1, training=False)
+        xe = t(x, dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        yy = m(xe)
+        (dxe,) = torch.autograd.grad(yy, xe, t(dy, dev))
+        assert rel_err(n(yy), ye) < TOL and rel_err(n(dxe), O.whiten_backward_eval(dy, we)) < TOL
+
+
+def test_resnet_tiny_channels_last_vs_reference_golden(dev):
+    import torch.nn.functional as Fn
+    import dwt_b200
+    from harness.resnet50_dwt import build_resnet50_dwt
+    from harness.synth import synth_batch, synth_state_dict
+    z = np.load(os.path.join(HERE, "resnet_tiny.npz"))
+    sd = {k: v.to(dev) for k, v in synth_state_dict(seed=1).items()}
+    x, labels = synth_batch(seed=2, per_domain=4, size=96)
+    model = build_resnet50_dwt(sd, dwt_b200, site_mode="fused", channels_last=True).to(dev).train()
+    logits = model(x.to(dev).contiguous(memory_format=torch.channels_last))
+    s, tt, a = torch.split(logits, logits.shape[0] // 3, dim=0)
+    cls = Fn.nll_loss(Fn.log_softmax(s, dim=1), labels.to(dev))
+    mec = 0.1 * dwt_b200.MinEntropyConsensusLoss(65, dev)(tt, a)
+    (cls + mec).backward()
+    assert rel_err(n(logits), z["logits"]) < 5e-3
+    assert abs(cls.item() - float(z["cls_loss"])) < 5e-3 and abs(mec.item() - float(z["mec_loss"])) < 5e-3
+    bufs = model.state_dict()
+    for k in [k[4:] for k in z.files if k.startswith("buf/")]:
+        assert rel_err(n(bufs[k]), z["buf/" + k]) < 1e-3, k
