@@ -163,16 +163,19 @@ __device__ __forceinline__ int acc_index(int g, int a) {
   return (g / NSUB) * (NSUB * PER) + (g % NSUB) * PER + a;
 }
 
-// one thread per group, all domains in order
+// One thread per (group, domain): blockDim = (64 groups, D).  The dense algebra of the D domains runs in
+// parallel; the running-statistic EMA is then applied by the d == 0 thread of each group for d = 0..D-1 in
+// order from shared memory (any aliasing pattern, no atomics).
 template <int GS>
-__global__ void __launch_bounds__(128) cl_fwd_finalize_kernel(const float* __restrict__ red, int S, const float* __restrict__ shift,
+__global__ void __launch_bounds__(256) cl_fwd_finalize_kernel(const float* __restrict__ red, int S, const float* __restrict__ shift,
                                                               const Geom gm, const FwdFin fin) {
   using SH = ClShape<GS>;
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= gm.G) return;
+  constexpr int NST = GS + GS * GS;
+  __shared__ float sStat[DWT_MAX_DOMAINS][64][NST + 1];
+  const int gl = threadIdx.x, d = threadIdx.y, g = blockIdx.x * 64 + gl;
   const int W = (gm.C >> 2) * SH::FWD;
   const float invM = 1.f / gm.M;
-  for (int d = 0; d < gm.D; ++d) {
+  if (g < gm.G) {
     float a[SH::FWD1];
 #pragma unroll
     for (int i = 0; i < SH::FWD1; ++i) {
@@ -190,9 +193,17 @@ __global__ void __launch_bounds__(128) cl_fwd_finalize_kernel(const float* __res
         const float c = a[GS + i * (i + 1) / 2 + j] * invM - (a[i] * invM) * (a[j] * invM);
         cov[i][j] = c; cov[j][i] = c;
       }
-    factor_thread<GS>(gm, fin, d, g, mean, cov, true);
-    ema_thread<GS>(gm, fin, d, g, mean, cov);
+    factor_thread<GS>(gm, fin, d, g, mean, cov, false);
+#pragma unroll
+    for (int i = 0; i < GS; ++i) {
+      sStat[d][gl][i] = mean[i];
+#pragma unroll
+      for (int j = 0; j < GS; ++j) sStat[d][gl][GS + i * GS + j] = cov[i][j];
+    }
   }
+  __syncthreads();
+  if (fin.update_running && d == 0 && g < gm.G)
+    for (int dd = 0; dd < gm.D; ++dd) ema_direct<GS>(gm, fin, dd, g, &sStat[dd][gl][0], &sStat[dd][gl][GS]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -315,13 +326,14 @@ __global__ void __launch_bounds__(kT, 2) cl_bwd_reduce_kernel(const float* __res
   }
 }
 
+// One thread per (group, domain), blockDim = (64, D); dgamma/dbeta are summed over the domains by the d == 0 thread
+// after the barrier.
 template <int GS>
-__global__ void __launch_bounds__(128) cl_bwd_finalize_kernel(const float* __restrict__ red, int S, const Geom gm, const BwdFin fin) {
+__global__ void __launch_bounds__(256) cl_bwd_finalize_kernel(const float* __restrict__ red, int S, const Geom gm, const BwdFin fin) {
   using SH = ClShape<GS>;
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= gm.G) return;
+  const int gl = threadIdx.x, d = threadIdx.y, g = blockIdx.x * 64 + gl;
   const int W = (gm.C >> 2) * SH::BWD;
-  for (int d = 0; d < gm.D; ++d) {
+  if (g < gm.G) {
     float R[GS][GS], sdz[GS];
 #pragma unroll
     for (int i = 0; i < SH::BWD1; ++i) {
@@ -330,7 +342,20 @@ __global__ void __launch_bounds__(128) cl_bwd_finalize_kernel(const float* __res
         for (int k = 0; k < S; ++k) s += red[((size_t)d * S + k) * W + acc_index<GS, SH::BWD1>(g, i)];
       if (i < GS * GS) R[i / GS][i % GS] = s; else sdz[i - GS * GS] = s;
     }
-    bwd_finalize_thread<GS>(gm, fin, d, g, R, sdz);
+    bwd_finalize_thread<GS>(gm, fin, d, g, R, sdz, false);
+  }
+  __syncthreads();
+  if ((fin.epi & DWT_EPI_AFFINE) && fin.dgamma != nullptr && d == 0 && g < gm.G) {
+#pragma unroll
+    for (int i = 0; i < GS; ++i) {
+      float sg = 0.f, sb = 0.f;
+      for (int dd = 0; dd < gm.D; ++dd) {
+        sg += fin.dgb_part[((size_t)dd * 2 + 0) * gm.C + g * GS + i];
+        sb += fin.dgb_part[((size_t)dd * 2 + 1) * gm.C + g * GS + i];
+      }
+      fin.dgamma[g * GS + i] = sg;
+      fin.dbeta[g * GS + i] = sb;
+    }
   }
 }
 
@@ -447,7 +472,7 @@ void cl_vec_reduce(const float* partial, int nrows, int W, int D, int S, float* 
   vec_reduce_kernel<<<dim3((W + 63) / 64, D, S), 256, 0, st>>>(partial, nrows, W, out);
 }
 void cl_fwd_finalize(const float* red, int S, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st) {
-  CL_GS(gm.GS, (cl_fwd_finalize_kernel<kGS><<<(gm.G + 127) / 128, 128, 0, st>>>(red, S, shift, gm, fin)));
+  CL_GS(gm.GS, (cl_fwd_finalize_kernel<kGS><<<(gm.G + 63) / 64, dim3(64, gm.D), 0, st>>>(red, S, shift, gm, fin)));
 }
 void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
               const float* gamma, const float* beta, cudaStream_t st) {
@@ -458,7 +483,7 @@ void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas,
   CL_GS(gm.GS, CL_EPI(epi, (cl_bwd_reduce_kernel<kGS, kEPI><<<cl_grid(gm, nctas), kT, 0, st>>>(x, dout, gm, mean, w, gamma, beta, partial))));
 }
 void cl_bwd_finalize(const float* red, int S, const Geom& gm, const BwdFin& fin, cudaStream_t st) {
-  CL_GS(gm.GS, (cl_bwd_finalize_kernel<kGS><<<(gm.G + 127) / 128, 128, 0, st>>>(red, S, gm, fin)));
+  CL_GS(gm.GS, (cl_bwd_finalize_kernel<kGS><<<(gm.G + 63) / 64, dim3(64, gm.D), 0, st>>>(red, S, gm, fin)));
 }
 void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, int epi, const float* coef,
                   const float* mean, const float* w, const float* gamma, const float* beta, cudaStream_t st) {

@@ -175,9 +175,24 @@ __device__ __forceinline__ void ema_thread(const Geom& gm, const FwdFin& f, int 
   }
 }
 
+// Plain read-modify-write EMA of domain d's buffers from registers.  Correct for ANY aliasing pattern when one
+// thread (or threads ordered by a barrier) applies the domains in order.
+template <int GS>
+__device__ __forceinline__ void ema_direct(const Geom& gm, const FwdFin& f, int d, int g, const float* mean,
+                                           const float* cov /* [GS*GS] row-major */) {
+  const float m = f.momentum, k = 1.f - f.momentum;
+  float* rc = f.rcov[d] + (size_t)g * GS * GS;
+  float* rm = f.rmean[d] + g * GS;
+#pragma unroll
+  for (int i = 0; i < GS; ++i) rm[i] = m * mean[i] + k * rm[i];
+#pragma unroll
+  for (int e = 0; e < GS * GS; ++e) rc[e] = m * (cov[e] * f.unbias) + k * rc[e];
+}
+
 template <int GS>
 __device__ __forceinline__ void bwd_finalize_thread(const Geom& gm, const BwdFin& f, int d, int g,
-                                                    const float (&R)[GS][GS], const float (&sdz)[GS]) {
+                                                    const float (&R)[GS][GS], const float (&sdz)[GS],
+                                                    bool combine_domains = true) {
   const size_t gbase = ((size_t)d * gm.G + g) * GS * GS;
   const int c0 = g * GS;
   const bool affine = (f.epi & DWT_EPI_AFFINE) != 0, train = f.mode == DWT_MODE_TRAIN;
@@ -258,7 +273,7 @@ __device__ __forceinline__ void bwd_finalize_thread(const Geom& gm, const BwdFin
     }
     coef[2 * GS * GS + i] = -c;
   }
-  if (affine && f.dgamma != nullptr) {
+  if (combine_domains && affine && f.dgamma != nullptr) {
     if (gm.D > 1) {
       __threadfence();
       const int t = atomicAdd(f.dom_counter + g, 1);

@@ -169,5 +169,9 @@ def build_resnet50_dwt(state_dict, layers, site_mode="modules", num_classes=65, 
     model = ResNet50DWT(layers, state_dict, num_classes=num_classes, site_mode=site_mode)
     model.load_state_dict(state_dict, strict=False)
     if channels_last:
-        model = model.to(memory_format=torch.channels_last)
+        # only the convolution weights: Module.to(memory_format=...) would also re-stride the [1,C,1,1]
+        # running-mean buffers into fresh tensors and silently break the aliasing of the three domain branches
+        for m in model.modules():
+            if isinstance(m, nn.Conv2d):
+                m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
     return model
