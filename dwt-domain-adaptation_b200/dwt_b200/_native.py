@@ -13,11 +13,11 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdwt_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_DOMAINS = 4
 MAX_GROUP_SIZE = 64
 MODE_TRAIN, MODE_EVAL = 0, 1
-EPI_NONE, EPI_AFFINE, EPI_RELU = 0, 1, 2
+EPI_NONE, EPI_AFFINE, EPI_RELU, EPI_RESIDUAL = 0, 1, 2, 4
 LAYOUT_NHWC = 0x100
 
 _c_float_p = ctypes.c_void_p
@@ -30,8 +30,8 @@ _SIGNATURES = {
     "dwt_whiten_fwd": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                       ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
-                                      _c_float_p, _c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p,
-                                      ctypes.c_size_t, ctypes.c_void_p]),
+                                      _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, _c_float_p, _c_float_p,
+                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "dwt_whiten_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                       _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, _c_float_p,
@@ -39,8 +39,8 @@ _SIGNATURES = {
     "dwt_bn_fwd": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                   ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int,
                                   ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), _c_float_p,
-                                  _c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t,
-                                  ctypes.c_void_p]),
+                                  _c_float_p, _c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p,
+                                  ctypes.c_size_t, ctypes.c_void_p]),
     "dwt_bn_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                   ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                   ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t,

@@ -272,8 +272,8 @@ int make_plan(Plan& p, KernelKind reduce_kind, KernelKind ew_kind, const void* a
 
 int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, int GS, int D, int mode, float a,
                     float b, float momentum, float unbias, int update_running, float* const* rmean,
-                    float* const* rcov, const float* gamma, const float* beta, int epi, float* save_mean,
-                    float* save_w, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    float* const* rcov, const float* gamma, const float* beta, const float* residual, int epi,
+                    float* save_mean, float* save_w, void* ws, size_t ws_bytes, cudaStream_t st) {
   const bool nhwc = (mode & DWT_LAYOUT_NHWC) != 0;
   mode &= 0xFF;
   Plan p;
@@ -285,6 +285,8 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
   if (mode != DWT_MODE_TRAIN && mode != DWT_MODE_EVAL) return fail(DWT_E_INVALID, "bad mode %d", mode);
   if ((epi & DWT_EPI_RELU) && !(epi & DWT_EPI_AFFINE)) return fail(DWT_E_INVALID, "RELU epilogue needs AFFINE");
   if ((epi & DWT_EPI_AFFINE) && (!gamma || !beta)) return fail(DWT_E_INVALID, "AFFINE epilogue needs gamma and beta");
+  if ((epi & DWT_EPI_RESIDUAL) && ((epi & 3) != 3 || !residual)) return fail(DWT_E_INVALID, "RESIDUAL epilogue needs AFFINE|RELU and a residual tensor");
+  if ((epi & DWT_EPI_RESIDUAL) && (uintptr_t)residual % 16 != 0) return fail(DWT_E_INVALID, "residual must be 16-byte aligned");
   if (epi != 0 && !p.small)
     return fail(DWT_E_UNSUPPORTED, "fused gamma/beta/ReLU epilogue is built for group_size 1, 2, 4 (got %d)", GS);
   const bool need_running = (mode == DWT_MODE_EVAL) || update_running;
@@ -333,7 +335,7 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
     if (int rc = check_launch("channels-last finalize kernel")) return rc;
     {
       Launch l("cl_apply", &p.gm, 2 * E, st);
-      dwt::cl_apply(x, y, p.gm, cp.new_, epi, save_mean, save_w, gamma, beta, st);
+      dwt::cl_apply(x, y, p.gm, cp.new_, epi, save_mean, save_w, gamma, beta, residual, st);
     }
     return check_launch("channels-last apply kernel");
   }
@@ -360,7 +362,7 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
   if (int rc = check_launch("whitening statistics kernel")) return rc;
   {
     Launch l(p.small ? "small_apply" : (tc ? "tc_apply" : "tiled_apply"), &p.gm, 2 * E, st);
-    if (p.small) dwt::small_apply(x, y, p.gm_ew, p.vec, p.chunks_ew, epi, save_mean, save_w, gamma, beta, st);
+    if (p.small) dwt::small_apply(x, y, p.gm_ew, p.vec, p.chunks_ew, epi, save_mean, save_w, gamma, beta, residual, st);
     else if (tc) {
       if (int cr = dwt::tc_apply(x, y, p.gm, tc_apply_ctas(p.gm, 2), save_mean, save_w, st))
         return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed (CUresult %d)", cr);
@@ -384,6 +386,7 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
   if (mode != DWT_MODE_TRAIN && mode != DWT_MODE_EVAL) return fail(DWT_E_INVALID, "bad mode %d", mode);
   if ((epi & DWT_EPI_RELU) && !(epi & DWT_EPI_AFFINE)) return fail(DWT_E_INVALID, "RELU epilogue needs AFFINE");
   if ((epi & DWT_EPI_AFFINE) && (!gamma || !beta)) return fail(DWT_E_INVALID, "AFFINE epilogue needs gamma and beta");
+  if (epi & DWT_EPI_RESIDUAL) return fail(DWT_E_INVALID, "backward of a RESIDUAL forward: pass dout already masked by (out > 0), epilogue AFFINE");
   if ((dgamma == nullptr) != (dbeta == nullptr)) return fail(DWT_E_INVALID, "dgamma and dbeta go together");
   if (epi != 0 && !p.small)
     return fail(DWT_E_UNSUPPORTED, "fused gamma/beta/ReLU epilogue is built for group_size 1, 2, 4 (got %d)", GS);
@@ -474,10 +477,10 @@ size_t dwt_workspace_bytes(int64_t N, int64_t C, int64_t HW, int group_size, int
 
 int dwt_whiten_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, int group_size, int n_domains,
                    int mode, float eps, float momentum, int update_running, float* const* running_mean,
-                   float* const* running_cov, const float* gamma, const float* beta, int epilogue, float* save_mean,
-                   float* save_w, void* workspace, size_t workspace_bytes, dwt_stream_t stream) {
+                   float* const* running_cov, const float* gamma, const float* beta, const float* residual, int epilogue,
+                   float* save_mean, float* save_w, void* workspace, size_t workspace_bytes, dwt_stream_t stream) {
   return whiten_like_fwd(x, y, N, C, HW, group_size, n_domains, mode, 1.f - eps, eps, momentum, 1.f, update_running,
-                         running_mean, running_cov, gamma, beta, epilogue, save_mean, save_w, workspace,
+                         running_mean, running_cov, gamma, beta, residual, epilogue, save_mean, save_w, workspace,
                          workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -493,12 +496,12 @@ int dwt_whiten_bwd(const float* x, const float* dout, float* dx, int64_t N, int6
 // S = var + eps, W = 1/sqrt(S) = invstd; only the EMA differs (unbiased variance).
 int dwt_bn_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, int n_domains, int mode, float eps,
                float factor, int update_running, float* const* running_mean, float* const* running_var,
-               const float* weight, const float* bias, int epilogue, float* save_mean, float* save_invstd,
-               void* workspace, size_t workspace_bytes, dwt_stream_t stream) {
+               const float* weight, const float* bias, const float* residual, int epilogue, float* save_mean,
+               float* save_invstd, void* workspace, size_t workspace_bytes, dwt_stream_t stream) {
   const double M = (double)N * (double)HW;
   const float unbias = M > 1.0 ? (float)(M / (M - 1.0)) : 1.f;
   return whiten_like_fwd(x, y, N, C, HW, 1, n_domains, mode, 1.f, eps, factor, unbias, update_running, running_mean,
-                         running_var, weight, bias, epilogue, save_mean, save_invstd, workspace, workspace_bytes,
+                         running_var, weight, bias, residual, epilogue, save_mean, save_invstd, workspace, workspace_bytes,
                          (cudaStream_t)stream);
 }
 

@@ -212,9 +212,11 @@ __global__ void __launch_bounds__(256) cl_fwd_finalize_kernel(const float* __res
 template <int GS, int EPI>
 __global__ void __launch_bounds__(kT, 3) cl_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const Geom gm,
                                                          const float* __restrict__ save_mean, const float* __restrict__ save_w,
-                                                         const float* __restrict__ gamma, const float* __restrict__ beta) {
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const float* __restrict__ res) {
   using S = ClShape<GS>;
-  constexpr int UNROLL = 8;
+  constexpr bool RES = (EPI & DWT_EPI_RESIDUAL) != 0;
+  constexpr int UNROLL = RES ? 4 : 8;
   const ClThread t(gm);
   const int d = blockIdx.z;
   float Wp[S::NSUB][S::NM], bp[S::NSUB][GS];
@@ -226,20 +228,25 @@ __global__ void __launch_bounds__(kT, 3) cl_apply_kernel(const float* __restrict
   }
   const size_t base = (size_t)d * gm.N * gm.HW * gm.C + 4 * t.q;
   const float* xd = x + base;
+  const float* rd = res + base;
   float* yd = y + base;
   for (unsigned r = t.r0 + t.rsub; r < t.r1; r += t.rpi * UNROLL) {
-    float4 v[UNROLL];
+    float4 v[UNROLL], rs[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const unsigned rr = r + u * t.rpi;
-      if (rr < t.r1) v[u] = ldg4(xd + (size_t)rr * gm.C);
+      if (rr < t.r1) {
+        v[u] = ldg4(xd + (size_t)rr * gm.C);
+        if constexpr (RES) rs[u] = ldg4(rd + (size_t)rr * gm.C);
+      }
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const unsigned rr = r + u * t.rpi;
       if (rr < t.r1) {
         const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-        float o[4];
+        float o[4], ra[4] = {0.f, 0.f, 0.f, 0.f};
+        if constexpr (RES) { ra[0] = rs[u].x; ra[1] = rs[u].y; ra[2] = rs[u].z; ra[3] = rs[u].w; }
 #pragma unroll
         for (int s = 0; s < S::NSUB; ++s) {
           float xi[GS], oi[GS];
@@ -247,7 +254,10 @@ __global__ void __launch_bounds__(kT, 3) cl_apply_kernel(const float* __restrict
           for (int c = 0; c < GS; ++c) xi[c] = e[s * GS + c];
           apply_group<GS>(Wp[s], bp[s], xi, oi);
 #pragma unroll
-          for (int c = 0; c < GS; ++c) o[s * GS + c] = (EPI & DWT_EPI_RELU) ? fmaxf(oi[c], 0.f) : oi[c];
+          for (int c = 0; c < GS; ++c) {
+            const float z = RES ? oi[c] + ra[s * GS + c] : oi[c];
+            o[s * GS + c] = (EPI & DWT_EPI_RELU) ? fmaxf(z, 0.f) : z;
+          }
         }
         *reinterpret_cast<float4*>(yd + (size_t)rr * gm.C) = make_float4(o[0], o[1], o[2], o[3]);
       }
@@ -475,8 +485,12 @@ void cl_fwd_finalize(const float* red, int S, const float* shift, const Geom& gm
   CL_GS(gm.GS, (cl_fwd_finalize_kernel<kGS><<<(gm.G + 63) / 64, dim3(64, gm.D), 0, st>>>(red, S, shift, gm, fin)));
 }
 void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
-              const float* gamma, const float* beta, cudaStream_t st) {
-  CL_GS(gm.GS, CL_EPI(epi, (cl_apply_kernel<kGS, kEPI><<<cl_grid(gm, nctas), kT, 0, st>>>(x, y, gm, mean, w, gamma, beta))));
+              const float* gamma, const float* beta, const float* residual, cudaStream_t st) {
+  if (epi == 7) {
+    CL_GS(gm.GS, (cl_apply_kernel<kGS, 7><<<cl_grid(gm, nctas), kT, 0, st>>>(x, y, gm, mean, w, gamma, beta, residual)));
+    return;
+  }
+  CL_GS(gm.GS, CL_EPI(epi, (cl_apply_kernel<kGS, kEPI><<<cl_grid(gm, nctas), kT, 0, st>>>(x, y, gm, mean, w, gamma, beta, nullptr))));
 }
 void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
                    const float* gamma, const float* beta, float* partial, cudaStream_t st) {

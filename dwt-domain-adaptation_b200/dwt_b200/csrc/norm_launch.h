@@ -10,7 +10,7 @@ void small_stats(const float* x, const Geom& gm, int vec, const FwdFin& fin, flo
                  cudaStream_t st);
 void small_eval_prep(const Geom& gm, const FwdFin& fin, cudaStream_t st);
 void small_apply(const float* x, float* y, const Geom& gm, int vec, int chunks, int epi, const float* mean,
-                 const float* w, const float* gamma, const float* beta, cudaStream_t st);
+                 const float* w, const float* gamma, const float* beta, const float* residual, cudaStream_t st);
 void small_bwd_reduce(const float* x, const float* dout, const Geom& gm, int vec, const BwdFin& fin,
                       const float* beta, float* partial, int* counters, cudaStream_t st);
 void small_bwd_prep(const Geom& gm, const BwdFin& fin, cudaStream_t st);
@@ -61,7 +61,7 @@ void cl_stats(const float* x, const Geom& gm, int nctas, float* partial, float* 
 void cl_vec_reduce(const float* partial, int nrows, int W, int D, int S, float* out, cudaStream_t st);
 void cl_fwd_finalize(const float* red, int S, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st);
 void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
-              const float* gamma, const float* beta, cudaStream_t st);
+              const float* gamma, const float* beta, const float* residual, cudaStream_t st);
 void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
                    const float* gamma, const float* beta, float* partial, cudaStream_t st);
 void cl_bwd_finalize(const float* red, int S, const Geom& gm, const BwdFin& fin, cudaStream_t st);

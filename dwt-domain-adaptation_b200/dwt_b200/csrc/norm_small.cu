@@ -211,8 +211,10 @@ __global__ void __launch_bounds__(kThreads, (GS * VEC >= 16) ? 3 : 4) small_appl
                                                                 const Geom gm, const float* __restrict__ save_mean,
                                                                 const float* __restrict__ save_w,
                                                                 const float* __restrict__ gamma,
-                                                                const float* __restrict__ beta) {
-  constexpr int NM = GS * (GS + 1) / 2, UNROLL = Unroll<GS, VEC>::stats;
+                                                                const float* __restrict__ beta,
+                                                                const float* __restrict__ res) {
+  constexpr bool RES = (EPI & DWT_EPI_RESIDUAL) != 0;
+  constexpr int NM = GS * (GS + 1) / 2, UNROLL = RES ? Unroll<GS, VEC>::one : Unroll<GS, VEC>::stats;
   const Team tm(gm);
   if (!tm.valid) return;
   const int g = tm.g, d = blockIdx.z;
@@ -224,8 +226,9 @@ __global__ void __launch_bounds__(kThreads, (GS * VEC >= 16) ? 3 : 4) small_appl
   float* yg = y + base;
   const ItemMap map{(unsigned)(gm.HW / VEC), (unsigned)(gm.C * gm.HW)};
   const unsigned items = (unsigned)gm.N * map.PV, stride = gridDim.x * tm.tthreads;
+  const float* rg = res + base;
   for (unsigned i0 = blockIdx.x * tm.tthreads + tm.ttid; i0 < items; i0 += stride * UNROLL) {
-    float v[UNROLL][GS][VEC];
+    float v[UNROLL][GS][VEC], rs[RES ? UNROLL : 1][GS][VEC];
     unsigned off[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -233,7 +236,10 @@ __global__ void __launch_bounds__(kThreads, (GS * VEC >= 16) ? 3 : 4) small_appl
       if (it < items) {
         off[u] = map.offset(it, VEC);
 #pragma unroll
-        for (int c = 0; c < GS; ++c) load_vec<VEC>(xg + off[u] + (size_t)c * gm.HW, v[u][c]);
+        for (int c = 0; c < GS; ++c) {
+          load_vec<VEC>(xg + off[u] + (size_t)c * gm.HW, v[u][c]);
+          if constexpr (RES) load_vec<VEC>(rg + off[u] + (size_t)c * gm.HW, rs[u][c]);
+        }
       }
     }
 #pragma unroll
@@ -248,7 +254,11 @@ __global__ void __launch_bounds__(kThreads, (GS * VEC >= 16) ? 3 : 4) small_appl
           for (int c = 0; c < GS; ++c) xi[c] = v[u][c][e];
           apply_group<GS>(Wp, bp, xi, oi);
 #pragma unroll
-          for (int c = 0; c < GS; ++c) o[c][e] = (EPI & DWT_EPI_RELU) ? fmaxf(oi[c], 0.f) : oi[c];
+          for (int c = 0; c < GS; ++c) {
+            float z = oi[c];
+            if constexpr (RES) z += rs[u][c][e];
+            o[c][e] = (EPI & DWT_EPI_RELU) ? fmaxf(z, 0.f) : z;
+          }
         }
 #pragma unroll
         for (int c = 0; c < GS; ++c) store_vec<VEC>(yg + off[u] + (size_t)c * gm.HW, o[c]);
@@ -480,9 +490,14 @@ void small_eval_prep(const Geom& gm, const FwdFin& fin, cudaStream_t st) {
 }
 
 void small_apply(const float* x, float* y, const Geom& gm, int vec, int chunks, int epi, const float* mean,
-                 const float* w, const float* gamma, const float* beta, cudaStream_t st) {
+                 const float* w, const float* gamma, const float* beta, const float* residual, cudaStream_t st) {
+  if (epi == 7) {
+    DWT_DISPATCH_GS(gm.GS, DWT_DISPATCH_VEC(vec, (small_apply_kernel<kGS, kVEC, 7><<<grid_of(gm, chunks), kThreads, 0, st>>>(
+                                                     x, y, gm, mean, w, gamma, beta, residual))));
+    return;
+  }
   DWT_DISPATCH_GS(gm.GS, DWT_DISPATCH_VEC(vec, DWT_DISPATCH_EPI(epi, (small_apply_kernel<kGS, kVEC, kEPI><<<grid_of(gm, chunks), kThreads, 0, st>>>(
-                                                                         x, y, gm, mean, w, gamma, beta)))));
+                                                                         x, y, gm, mean, w, gamma, beta, nullptr)))));
 }
 
 void small_bwd_reduce(const float* x, const float* dout, const Geom& gm, int vec, const BwdFin& fin,

@@ -35,7 +35,7 @@ class _NormFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, kind, group_size, n_domains, mode, eps, momentum, update_running,
+    def forward(ctx, x, gamma, beta, residual, kind, group_size, n_domains, mode, eps, momentum, update_running,
                 running, relu):
         lib = nv.lib()
         gs = group_size if kind == "whiten" else 1
@@ -44,10 +44,14 @@ class _NormFunction(torch.autograd.Function):
         if n_all % n_domains != 0:
             raise ValueError(f"batch of {n_all} does not split into {n_domains} domains")
         n = n_all // n_domains
-        dev = nv.require_cuda(x, gamma, beta, *[t for pair in running for t in pair])
+        dev = nv.require_cuda(x, gamma, beta, residual, *[t for pair in running for t in pair])
         epi = nv.EPI_NONE
+        if residual is not None:
+            if gamma is None or not relu or residual.shape != x.shape:
+                raise ValueError("a fused residual needs gamma/beta, relu=True and a tensor shaped like x")
+            residual = residual.contiguous(memory_format=torch.channels_last) if nhwc else residual.contiguous()
         if gamma is not None:
-            epi = nv.EPI_AFFINE | (nv.EPI_RELU if relu else 0)
+            epi = nv.EPI_AFFINE | (nv.EPI_RELU if relu else 0) | (nv.EPI_RESIDUAL if residual is not None else 0)
             gamma_c, beta_c = gamma.detach().reshape(-1).contiguous(), beta.detach().reshape(-1).contiguous()
         else:
             gamma_c = beta_c = None
@@ -61,26 +65,38 @@ class _NormFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             if kind == "whiten":
                 rc = lib.dwt_whiten_fwd(nv.ptr(x), nv.ptr(y), n, c, hw, gs, n_domains, mode | layout, eps, momentum,
-                                        int(update_running), rm, rv, nv.ptr(gamma_c), nv.ptr(beta_c), epi,
+                                        int(update_running), rm, rv, nv.ptr(gamma_c), nv.ptr(beta_c), nv.ptr(residual), epi,
                                         nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
             else:
                 rc = lib.dwt_bn_fwd(nv.ptr(x), nv.ptr(y), n, c, hw, n_domains, mode | layout, eps, momentum,
-                                    int(update_running), rm, rv, nv.ptr(gamma_c), nv.ptr(beta_c), epi,
+                                    int(update_running), rm, rv, nv.ptr(gamma_c), nv.ptr(beta_c), nv.ptr(residual), epi,
                                     nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
         nv.check(rc)
-        ctx.save_for_backward(x, save_mean, save_w, gamma_c, beta_c)
+        if residual is not None:
+            # backward of relu(z + residual): dz = dout * (out > 0) is also the residual's gradient; the norm's own
+            # backward then runs on dz with the plain affine epilogue -- same bytes as masking inside the kernels
+            ctx.save_for_backward(x, save_mean, save_w, gamma_c, beta_c, y)
+            epi = nv.EPI_AFFINE
+        else:
+            ctx.save_for_backward(x, save_mean, save_w, gamma_c, beta_c)
+        ctx.has_residual = residual is not None
         ctx.cfg = (kind, gs, n_domains, mode | layout, eps, epi, n, c, hw, None if gamma is None else gamma.shape)
         return y
 
     @staticmethod
     def backward(ctx, dout):
         lib = nv.lib()
-        x, save_mean, save_w, gamma_c, beta_c = ctx.saved_tensors
+        if ctx.has_residual:
+            x, save_mean, save_w, gamma_c, beta_c, out = ctx.saved_tensors
+            dout = torch.ops.aten.threshold_backward(dout, out, 0)
+        else:
+            x, save_mean, save_w, gamma_c, beta_c = ctx.saved_tensors
         kind, gs, n_domains, mode, eps, epi, n, c, hw, gshape = ctx.cfg
         dout = dout.contiguous(memory_format=torch.channels_last) if (mode & nv.LAYOUT_NHWC) else dout.contiguous()
         dev = nv.require_cuda(dout)
         dx = torch.empty_like(x)
         want_affine = gamma_c is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        d_res = dout if (ctx.has_residual and ctx.needs_input_grad[3]) else None
         dgamma = torch.empty(c, dtype=torch.float32, device=dev) if want_affine else None
         dbeta = torch.empty(c, dtype=torch.float32, device=dev) if want_affine else None
         ws = nv.workspace(dev, n, c, hw, gs, n_domains)
@@ -96,14 +112,14 @@ class _NormFunction(torch.autograd.Function):
         nv.check(rc)
         if want_affine:
             dgamma, dbeta = dgamma.view(gshape), dbeta.view(gshape)
-        return (dx, dgamma, dbeta) + (None,) * 9
+        return (dx, dgamma, dbeta, d_res) + (None,) * 9
 
 
 def norm(x, gamma, beta, *, kind, group_size, n_domains, training_stats, eps, momentum, update_running,
-         running, relu=False):
+         running, relu=False, residual=None):
     mode = nv.MODE_TRAIN if training_stats else nv.MODE_EVAL
-    return _NormFunction.apply(x, gamma, beta, kind, group_size, n_domains, mode, float(eps), float(momentum),
-                               bool(update_running), running, bool(relu))
+    return _NormFunction.apply(x, gamma, beta, residual, kind, group_size, n_domains, mode, float(eps),
+                               float(momentum), bool(update_running), running, bool(relu))
 
 
 class _MecFunction(torch.autograd.Function):

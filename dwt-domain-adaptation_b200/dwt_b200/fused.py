@@ -30,9 +30,11 @@ class DomainTripleNorm(nn.Module):
             raise NotImplementedError("the fused site is built for group sizes 1, 2 and 4 "
                                       f"(got {self.group_size}); use the per-domain modules")
 
-    def forward(self, x, domain_modules, gamma, beta, relu=False):
+    def forward(self, x, domain_modules, gamma, beta, relu=False, residual=None):
         """x: [n_domains*N, C, H, W]; domain_modules: the per-domain WTransform2d / BatchNorm2d
-        modules (training mode), whose buffers receive the EMA updates; gamma/beta: [C,1,1]."""
+        modules (training mode), whose buffers receive the EMA updates; gamma/beta: [C,1,1];
+        residual (needs relu=True): out = relu(norm(x)*gamma + beta + residual), the Bottleneck tail
+        (resnet50_dwt_mec_officehome.py:239-240) folded into the apply pass."""
         mods = list(domain_modules)
         if len(mods) != self.n_domains:
             raise ValueError(f"expected {self.n_domains} domain modules")
@@ -52,4 +54,4 @@ class DomainTripleNorm(nn.Module):
         update = m0.training and m0.track_running_stats
         return F.norm(x, gamma, beta, kind=self.kind, group_size=self.group_size, n_domains=self.n_domains,
                       training_stats=True, eps=eps, momentum=momentum, update_running=update,
-                      running=running, relu=relu)
+                      running=running, relu=relu, residual=residual)

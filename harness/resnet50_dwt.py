@@ -86,9 +86,17 @@ class _SiteOwner(nn.Module):
                 kind="whiten" if whiten else "bn", num_features=planes,
                 group_size=group_size if whiten else 1))
 
-    def _site(self, tag, x, relu):
+    def _site(self, tag, x, relu, residual=None):
+        """residual: the Bottleneck tail `relu(site(x) + identity)`; folded into the kernel by the fused site,
+        applied with ATen ops otherwise."""
         names, gname, bname, whiten = self._sites[tag]
         gamma, beta = getattr(self, gname), getattr(self, bname)
+        if residual is not None:
+            fused = getattr(self, f"_fused_{tag}", None) if self.training else None
+            if fused is not None:
+                mods = [getattr(self, n) for n in names]
+                return fused(x, [m.wh if whiten else m for m in mods], gamma, beta, True, residual=residual)
+            return torch.relu_(self._site(tag, x, relu=False) + residual)
         if self.training:
             fused = getattr(self, f"_fused_{tag}", None)
             mods = [getattr(self, n) for n in names]
@@ -122,9 +130,8 @@ class Bottleneck(_SiteOwner):
     def forward(self, x):
         out = self._site("1", self.conv1(x), relu=True)
         out = self._site("2", self.conv2(out), relu=True)
-        out = self._site("3", self.conv3(out), relu=False)
         identity = x if self.downsample is None else self._site("downsample", self.downsample(x), relu=False)
-        return torch.relu_(out + identity)
+        return self._site("3", self.conv3(out), relu=True, residual=identity)
 
 
 class ResNet50DWT(_SiteOwner):

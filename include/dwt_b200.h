@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DWT_B200_ABI_VERSION 1
+#define DWT_B200_ABI_VERSION 2
 #define DWT_MAX_DOMAINS 4
 #define DWT_MAX_GROUP_SIZE 64
 
@@ -60,6 +60,8 @@ extern "C" {
 #define DWT_EPI_NONE 0
 #define DWT_EPI_AFFINE 1 /* out = y * gamma[c] + beta[c]        */
 #define DWT_EPI_RELU 2   /* out = max(out, 0)  (needs AFFINE)   */
+#define DWT_EPI_RESIDUAL 4 /* forward only: out = max(y*gamma + beta + residual, 0)  (needs AFFINE|RELU);
+                              the Bottleneck tail `relu(bn3(conv3) + identity)`, resnet50_dwt_mec_officehome.py:239-240 */
 
 typedef struct CUstream_st *dwt_stream_t; /* == cudaStream_t */
 
@@ -89,6 +91,7 @@ DWT_API size_t dwt_workspace_bytes(int64_t N, int64_t C, int64_t HW, int group_s
  *   save_mean       [n_domains, C]            mean used (batch or running)
  *   save_w          [n_domains, C/gs, gs, gs] W = inverse(cholesky((1-eps) cov + eps I))
  *   gamma, beta     [C] or NULL (epilogue)
+ *   residual        same shape/layout as x, or NULL (DWT_EPI_RESIDUAL)
  * TRAIN: batch mean/cov; when update_running, the EMA r = (1-m) r + m stat is applied
  * domain by domain in order (so aliased buffers see s, then t, then t_aug --
  * SURVEY.md H5), on the UN-shrunk covariance (whitening.py:57-59).
@@ -97,7 +100,7 @@ DWT_API size_t dwt_workspace_bytes(int64_t N, int64_t C, int64_t HW, int group_s
 DWT_API int dwt_whiten_fwd(const float *x, float *y, int64_t N, int64_t C, int64_t HW, int group_size,
                    int n_domains, int mode, float eps, float momentum, int update_running,
                    float *const *running_mean, float *const *running_cov, const float *gamma,
-                   const float *beta, int epilogue, float *save_mean, float *save_w,
+                   const float *beta, const float *residual, int epilogue, float *save_mean, float *save_w,
                    void *workspace, size_t workspace_bytes, dwt_stream_t stream);
 
 /*
@@ -119,8 +122,8 @@ DWT_API int dwt_whiten_bwd(const float *x, const float *dout, float *dx, int64_t
  */
 DWT_API int dwt_bn_fwd(const float *x, float *y, int64_t N, int64_t C, int64_t HW, int n_domains, int mode,
                float eps, float factor, int update_running, float *const *running_mean,
-               float *const *running_var, const float *weight, const float *bias, int epilogue,
-               float *save_mean, float *save_invstd, void *workspace, size_t workspace_bytes,
+               float *const *running_var, const float *weight, const float *bias, const float *residual,
+               int epilogue, float *save_mean, float *save_invstd, void *workspace, size_t workspace_bytes,
                dwt_stream_t stream);
 
 DWT_API int dwt_bn_bwd(const float *x, const float *dout, float *dx, int64_t N, int64_t C, int64_t HW,

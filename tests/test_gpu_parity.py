@@ -495,3 +495,39 @@ def test_resnet_tiny_channels_last_vs_reference_golden(dev):
     bufs = model.state_dict()
     for k in [k[4:] for k in z.files if k.startswith("buf/")]:
         assert rel_err(n(bufs[k]), z["buf/" + k]) < 1e-3, k
+
+
+@pytest.mark.parametrize("fmt", ["nchw", "nhwc"])
+@pytest.mark.parametrize("kind,c,hw,gs", [("whiten", 64, 14, 4), ("bn", 256, 7, 1)])
+def test_fused_residual_tail_equals_unfused(kind, c, hw, gs, fmt, dev):
+    """out = relu(site(x)*gamma + beta + identity) folded into the apply pass (Bottleneck tail,
+    resnet50_dwt_mec_officehome.py:239-240) vs the same site followed by ATen add + relu: outputs and every
+    gradient (x, identity, gamma, beta) must agree to rounding."""
+    import batch_norm
+    import whitening
+    from dwt_b200 import DomainTripleNorm
+    torch.manual_seed(3)
+    nper = 4
+    mk = (lambda a: a.contiguous(memory_format=torch.channels_last)) if fmt == "nhwc" else (lambda a: a.contiguous())
+    x0 = mk(torch.randn(3 * nper, c, hw, hw, device=dev) * 1.5 + 0.3)
+    r0 = mk(torch.randn(3 * nper, c, hw, hw, device=dev))
+    dout = mk(torch.randn(3 * nper, c, hw, hw, device=dev))
+    g0, b0 = torch.rand(c, 1, 1, device=dev) + 0.5, 0.2 * torch.randn(c, 1, 1, device=dev)
+    res = {}
+    for mode in ("fused", "unfused"):
+        if kind == "whiten":
+            mods = [whitening.WTransform2d(c, gs).to(dev).train() for _ in range(3)]
+        else:
+            rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+            mods = [batch_norm.BatchNorm2d(c, rm, rv, affine=False).train() for _ in range(3)]
+        site = DomainTripleNorm(kind, c, gs)
+        x, r = x0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+        g, b = g0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        if mode == "fused":
+            out = site(x, mods, g, b, relu=True, residual=r)
+        else:
+            out = torch.relu(site(x, mods, g, b, relu=False) + r)
+        out.backward(dout)
+        res[mode] = [out.detach(), x.grad, r.grad, g.grad, b.grad]
+    for a, bb in zip(res["fused"], res["unfused"]):
+        assert rel_err(n(a), n(bb)) < 1e-5
