@@ -334,7 +334,7 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
     }
     if (int rc = check_launch("channels-last finalize kernel")) return rc;
     {
-      Launch l("cl_apply", &p.gm, 2 * E, st);
+      Launch l("cl_apply", &p.gm, ((epi & DWT_EPI_RESIDUAL) ? 3 : 2) * E, st);
       dwt::cl_apply(x, y, p.gm, cp.new_, epi, save_mean, save_w, gamma, beta, residual, st);
     }
     return check_launch("channels-last apply kernel");
@@ -361,7 +361,7 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
   }
   if (int rc = check_launch("whitening statistics kernel")) return rc;
   {
-    Launch l(p.small ? "small_apply" : (tc ? "tc_apply" : "tiled_apply"), &p.gm, 2 * E, st);
+    Launch l(p.small ? "small_apply" : (tc ? "tc_apply" : "tiled_apply"), &p.gm, ((epi & DWT_EPI_RESIDUAL) ? 3 : 2) * E, st);
     if (p.small) dwt::small_apply(x, y, p.gm_ew, p.vec, p.chunks_ew, epi, save_mean, save_w, gamma, beta, residual, st);
     else if (tc) {
       if (int cr = dwt::tc_apply(x, y, p.gm, tc_apply_ctas(p.gm, 2), save_mean, save_w, st))

@@ -22,9 +22,9 @@ def gpu(site_mode):
     from harness.synth import synth_batch
     dev = torch.device("cuda", 0)
     torch.backends.cudnn.benchmark = True
-    model = bench.build_model(dwt_b200, dev, site_mode)
+    model = bench.build_model(dwt_b200, dev, site_mode, channels_last=True)
     opt = bench.make_optimizer(model); mec = dwt_b200.MinEntropyConsensusLoss(65, dev)
-    im, lb = synth_batch(3, 64); im, lb = im.to(dev), lb.to(dev)
+    im, lb = synth_batch(3, 64); im, lb = im.to(dev).contiguous(memory_format=torch.channels_last), lb.to(dev)
     for _ in range(3): bench.train_step(model, mec, opt, im, lb)
     torch.cuda.synchronize()
     from torch.profiler import profile, ProfilerActivity
