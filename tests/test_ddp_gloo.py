@@ -1,9 +1,9 @@
 """World-size-2 data-parallel step on CPU (gloo): the N>1 path of bench.py without a GPU.
 
 The product layers have no CPU path, so the harness model is built on the CPU port of the
-reference layers (oracle/torch_port.py) -- what is under test is the host-side plumbing: one
-process per rank, rank-local whitening statistics (buffers NOT broadcast), gradients averaged by
-the all-reduce, SURVEY.md §8e.
+reference layers (oracle/torch_port.py) -- what is under test is the host-side plumbing of
+bench.py (FlatGradAllReduce + train_step): one process per rank, rank-local whitening statistics
+(never exchanged), gradients averaged by one flat all-reduce, SURVEY.md §8e.
 """
 import os
 import socket
@@ -26,15 +26,11 @@ def _step(rank_seed, ddp):
     torch.manual_seed(0)
     torch.set_num_threads(2)
     model = bench.build_model(port, torch.device("cpu"), "modules")
-    net = torch.nn.parallel.DistributedDataParallel(model, broadcast_buffers=False) if ddp else model
-    opt = bench.make_optimizer(model)
+    sync = bench.FlatGradAllReduce(model, 2) if ddp else None      # the data-parallel plumbing of bench.py
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)               # lr 0: inspect the synchronised gradients
     mec = port.MinEntropyConsensusLoss(bench.NUM_CLASSES, "cpu")
     images, labels = synth_batch(seed=rank_seed, per_domain=1, size=64)
-    opt.zero_grad(set_to_none=True)
-    logits = net(images)
-    s, t, a = torch.split(logits, 1, dim=0)
-    loss = torch.nn.functional.nll_loss(torch.log_softmax(s, 1), labels) + bench.LAMBDA_MEC * mec(t, a)
-    loss.backward()
+    bench.train_step(model, mec, opt, images, labels, sync)
     params = dict(model.named_parameters())
     return {k: params[k].grad.clone() for k in PICK}, model.state_dict()["bns1.wh.running_mean"].clone()
 
