@@ -255,6 +255,17 @@ def timed_loop(step_fn, steps, device, distributed):
     return float(ms.item())
 
 
+def finish(distributed, device):
+    """Leave a multi-rank run without tearing NCCL down: destroying a process group whose collectives were
+    captured into a live CUDA graph can dead-lock, and a benchmark that hangs after printing its line is worse
+    than one that skips destructors."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if distributed:
+        torch.cuda.synchronize(device)
+        os._exit(0)
+
+
 def run_ours(args):
     import torch.distributed as dist
     import dwt_b200
@@ -380,8 +391,7 @@ def run_ours(args):
     value = per_gpu * world * args.steps / (ms / 1e3)
     e2e = per_gpu * world * args.steps / (ms_e2e / 1e3)
     if rank != 0:
-        if distributed:
-            dist.destroy_process_group()
+        finish(distributed, device)
         return
     peak, peak_src = measured_peaks()
     if args.sites_out:
@@ -418,8 +428,7 @@ def run_ours(args):
     if args.cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(out))
-    if distributed:
-        dist.destroy_process_group()
+    finish(distributed, device)
 
 
 def run_microbench(args, device, rank):
