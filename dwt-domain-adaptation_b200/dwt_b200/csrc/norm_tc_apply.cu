@@ -76,7 +76,7 @@ __device__ __forceinline__ void split_box(float* hi, float* lo, int tt, const fl
 // for l >= 16, so the two halves that must be added end up 16 lanes apart IN THE SAME WARP and the
 // epilogue folds them with one shuffle per value -- no shared-memory staging at all.
 template <int NIN>
-__global__ void __launch_bounds__(kApThreads, 1)
+__global__ void __launch_bounds__(kApThreads, NIN == 1 ? 2 : 1)
 tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Geom gm,
                 const ApplyArgs args) {
   constexpr int STAGES = 3;       // NIN = 1: 97 KB -> two CTAs per SM; NIN = 2: 193 KB -> one
@@ -265,6 +265,9 @@ int tc_apply_init() {
   g_encode_ap = reinterpret_cast<EncodeTiledFn>(fn);
   e = cudaFuncSetAttribute(tc_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ap_smem<1>());
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ap_smem<2>());
+  // two 97 KB CTAs per SM need the full shared-memory carve-out
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_apply_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_apply_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   return (int)e;
 }
 
