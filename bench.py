@@ -164,14 +164,18 @@ class FlatGradAllReduce:
                 self.flat.div_(self.world)
 
 
-def train_step(model, mec, opt, images, labels, sync=None):
+def train_step(model, mec, opt, images, labels, sync=None, head=None):
+    """head: dwt_b200.HeadLoss -- the same NLL + lambda*MEC as one fused launch (GPU arm)."""
     if sync is None:
         opt.zero_grad(set_to_none=True)
     else:
         sync.zero()
     logits = model(images)
-    src, tgt, aug = torch.split(logits, logits.shape[0] // 3, dim=0)
-    loss = F.nll_loss(F.log_softmax(src, dim=1), labels) + LAMBDA_MEC * mec(tgt, aug)
+    if head is not None:
+        loss = head(logits, labels)
+    else:
+        src, tgt, aug = torch.split(logits, logits.shape[0] // 3, dim=0)
+        loss = F.nll_loss(F.log_softmax(src, dim=1), labels) + LAMBDA_MEC * mec(tgt, aug)
     loss.backward()
     if sync is not None:
         sync.reduce()
@@ -303,6 +307,7 @@ def run_ours(args):
     sync = FlatGradAllReduce(model, world)
     opt = make_optimizer(model)
     mec = dwt_b200.MinEntropyConsensusLoss(NUM_CLASSES, device)
+    head = dwt_b200.HeadLoss(NUM_CLASSES, LAMBDA_MEC)
     B = args.per_domain
     host_images, host_labels = synth_batch(seed=100 + rank, per_domain=B)
     if nhwc:
@@ -312,12 +317,12 @@ def run_ours(args):
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
 
     def step_resident():
-        train_step(net, mec, opt, images, labels, sync)
+        train_step(net, mec, opt, images, labels, sync, head)
 
     def step_e2e():
         im = host_images.to(device, non_blocking=True)
         lb = host_labels.to(device, non_blocking=True)
-        loss = train_step(net, mec, opt, im, lb, sync)
+        loss = train_step(net, mec, opt, im, lb, sync, head)
         loss_host.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream(device).synchronize()     # the user reads the loss every step
 
@@ -346,7 +351,7 @@ def run_ours(args):
             torch.cuda.synchronize(device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_loss = train_step(net, mec, opt, images, labels, sync)
+                static_loss = train_step(net, mec, opt, images, labels, sync, head)
             torch.cuda.synchronize(device)
         except Exception as e:                      # capture is an optimisation, never a requirement
             graph = None

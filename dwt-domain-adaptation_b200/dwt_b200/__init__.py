@@ -6,9 +6,9 @@ the reference's ``utils/`` and the reference scripts' ``import whitening`` / ``i
 """
 from . import _native
 from .batch_norm import BatchNorm1d, BatchNorm2d, BatchNorm3d
-from .consensus_loss import MinEntropyConsensusLoss
+from .consensus_loss import HeadLoss, MinEntropyConsensusLoss
 from .fused import DomainTripleNorm
 from .whitening import WTransform2d
 
 __all__ = ["WTransform2d", "BatchNorm1d", "BatchNorm2d", "BatchNorm3d", "MinEntropyConsensusLoss",
-           "DomainTripleNorm", "_native"]
+           "DomainTripleNorm", "HeadLoss", "_native"]

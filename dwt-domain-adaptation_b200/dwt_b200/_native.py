@@ -47,6 +47,8 @@ _SIGNATURES = {
                                   ctypes.c_void_p]),
     "dwt_mec_fwd_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, _c_float_p,
                                        _c_float_p, _c_float_p, ctypes.c_void_p]),
+    "dwt_head_loss_fwd_bwd": (ctypes.c_int, [_c_float_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_float,
+                                             _c_float_p, _c_float_p, ctypes.c_void_p]),
     "dwt_launch_count": (ctypes.c_int64, []),
     "dwt_profile_begin": (None, []),
     "dwt_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

@@ -524,6 +524,17 @@ int dwt_mec_fwd_bwd(const float* x, const float* y, int64_t N, int64_t K, float*
   return check_launch("MEC kernel");
 }
 
+int dwt_head_loss_fwd_bwd(const float* logits, const int64_t* labels, int64_t B, int64_t K, float lambda, float* losses,
+                          float* grad, dwt_stream_t stream) {
+  if (!logits || !labels || !losses || !grad) return fail(DWT_E_INVALID, "null pointer argument");
+  if (B <= 0 || K <= 0 || B >= (1 << 22) || K >= (1 << 24)) return fail(DWT_E_INVALID, "bad logits shape [3*%lld,%lld]", (long long)B, (long long)K);
+  {
+    Launch l("head_loss", nullptr, 4.0 * 3 * (double)B * (double)K * 2, (cudaStream_t)stream);
+    dwt::head_loss_launch(logits, reinterpret_cast<const long long*>(labels), (int)B, (int)K, lambda, losses, grad, (cudaStream_t)stream);
+  }
+  return check_launch("head loss kernel");
+}
+
 int64_t dwt_launch_count(void) { return g_launches.load(); }
 
 void dwt_profile_begin(void) {

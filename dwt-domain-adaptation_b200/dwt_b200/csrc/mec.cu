@@ -67,7 +67,80 @@ __global__ void __launch_bounds__(kMecThreads) mec_kernel(const float* __restric
   }
 }
 
+// Head loss of the training step in one launch (resnet50_dwt_mec_officehome.py:421-428):
+//   logits [3B, K] = source | target | target-aug ;  labels [B]
+//   loss = mean_n NLL(log_softmax(source_n), label_n) + lambda * MEC(target, target-aug)
+// losses[0..2] = total, classification, lambda*MEC ; grad [3B, K] = d total / d logits.
+__global__ void __launch_bounds__(kMecThreads) head_loss_kernel(const float* __restrict__ logits,
+                                                                 const long long* __restrict__ labels, int B, int K,
+                                                                 float lambda, float* __restrict__ losses,
+                                                                 float* __restrict__ grad) {
+  __shared__ float sCls[kMecThreads / 32], sMec[kMecThreads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float cls = 0.f, mec = 0.f;
+  for (int n = warp; n < 2 * B; n += nwarps) {
+    if (n < B) {                                   // source row: softmax cross-entropy
+      const float* xr = logits + (size_t)n * K;
+      float mx = -FLT_MAX;
+      for (int k = lane; k < K; k += 32) mx = fmaxf(mx, xr[k]);
+      mx = warp_max(mx);
+      float sx = 0.f;
+      for (int k = lane; k < K; k += 32) sx += expf(xr[k] - mx);
+      sx = warp_sum(sx);
+      const float lz = mx + logf(sx);
+      const int y = (int)labels[n];
+      cls += (lane == 0) ? (lz - xr[y]) : 0.f;
+      const float sc = 1.f / (float)B;
+      for (int k = lane; k < K; k += 32) grad[(size_t)n * K + k] = sc * (expf(xr[k] - lz) - (k == y ? 1.f : 0.f));
+    } else {                                       // target row n and its augmented twin n + B: MEC
+      const float* xr = logits + (size_t)n * K;
+      const float* yr = logits + (size_t)(n + B) * K;
+      float mx = -FLT_MAX, my = -FLT_MAX;
+      for (int k = lane; k < K; k += 32) { mx = fmaxf(mx, xr[k]); my = fmaxf(my, yr[k]); }
+      mx = warp_max(mx); my = warp_max(my);
+      float sx = 0.f, sy = 0.f;
+      for (int k = lane; k < K; k += 32) { sx += expf(xr[k] - mx); sy += expf(yr[k] - my); }
+      sx = warp_sum(sx); sy = warp_sum(sy);
+      const float lzx = mx + logf(sx), lzy = my + logf(sy);
+      float best = FLT_MAX; int bk = 0x7fffffff;
+      for (int k = lane; k < K; k += 32) {
+        const float s = -0.5f * ((xr[k] - lzx) + (yr[k] - lzy));
+        if (s < best) { best = s; bk = k; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        if (ob < best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+      }
+      mec += (lane == 0) ? best : 0.f;
+      const float sc = lambda * 0.5f / (float)B;
+      for (int k = lane; k < K; k += 32) {
+        const float hot = (k == bk) ? 1.f : 0.f;
+        grad[(size_t)n * K + k] = sc * (expf(xr[k] - lzx) - hot);
+        grad[(size_t)(n + B) * K + k] = sc * (expf(yr[k] - lzy) - hot);
+      }
+    }
+  }
+  if (lane == 0) { sCls[warp] = cls; sMec[warp] = mec; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float c = 0.f, m = 0.f;
+    for (int w = 0; w < nwarps; ++w) { c += sCls[w]; m += sMec[w]; }
+    c /= (float)B; m = lambda * m / (float)B;
+    losses[0] = c + m; losses[1] = c; losses[2] = m;
+  }
+}
+
 }  // namespace
+
+void head_loss_launch(const float* logits, const long long* labels, int B, int K, float lambda, float* losses,
+                      float* grad, cudaStream_t st) {
+  int threads = 2 * B * 32;
+  if (threads > kMecThreads) threads = kMecThreads;
+  if (threads < 32) threads = 32;
+  head_loss_kernel<<<1, threads, 0, st>>>(logits, labels, B, K, lambda, losses, grad);
+}
 
 void mec_launch(const float* x, const float* y, int N, int K, float* loss, float* gx, float* gy, cudaStream_t st) {
   int threads = N * 32;

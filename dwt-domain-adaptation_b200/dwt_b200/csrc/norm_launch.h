@@ -69,6 +69,8 @@ void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, 
                   const float* mean, const float* w, const float* gamma, const float* beta, cudaStream_t st);
 
 // MEC loss (mec.cu)
+void head_loss_launch(const float* logits, const long long* labels, int B, int K, float lambda, float* losses,
+                      float* grad, cudaStream_t st);
 void mec_launch(const float* x, const float* y, int N, int K, float* loss, float* gx, float* gy, cudaStream_t st);
 
 }  // namespace dwt

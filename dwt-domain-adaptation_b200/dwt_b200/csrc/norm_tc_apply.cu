@@ -223,13 +223,26 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
       const int t = t_begin + it, n = t / PB, pb = t - n * PB, px0 = pb * kTilePxA;
       if (lane < 16 && ch < gm.C) {
         float* orow = args.out + ((size_t)(d * gm.N + n) * gm.C + ch) * gm.HW + px0;
+        if ((gm.HW & 7) == 0) {
+          // 256-bit stores (sm_100 STG.256): every instruction writes whole 32-byte sectors of this thread's row;
+          // 128-bit stores left half-written sectors behind (16 sectors per request, 2x the L2 write traffic)
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4)
-            if (px0 + h * 32 + 4 * c4 < gm.HW)
-              *reinterpret_cast<float4*>(orow + h * 32 + 4 * c4) =
-                  make_float4(v[h][4 * c4], v[h][4 * c4 + 1], v[h][4 * c4 + 2], v[h][4 * c4 + 3]);
+            for (int c8 = 0; c8 < 4; ++c8)
+              if (px0 + h * 32 + 8 * c8 < gm.HW)
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + h * 32 + 8 * c8),
+                             "f"(v[h][8 * c8]), "f"(v[h][8 * c8 + 1]), "f"(v[h][8 * c8 + 2]), "f"(v[h][8 * c8 + 3]),
+                             "f"(v[h][8 * c8 + 4]), "f"(v[h][8 * c8 + 5]), "f"(v[h][8 * c8 + 6]), "f"(v[h][8 * c8 + 7]) : "memory");
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4)
+              if (px0 + h * 32 + 4 * c4 < gm.HW)
+                *reinterpret_cast<float4*>(orow + h * 32 + 4 * c4) =
+                    make_float4(v[h][4 * c4], v[h][4 * c4 + 1], v[h][4 * c4 + 2], v[h][4 * c4 + 3]);
+        }
       }
     }
   }

@@ -147,3 +147,35 @@ class _MecFunction(torch.autograd.Function):
 
 def mec_loss(x, y):
     return _MecFunction.apply(x, y)
+
+
+class _HeadLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, lam):
+        lib = nv.lib()
+        if logits.dim() != 2 or logits.shape[0] % 3 != 0 or labels.dim() != 1 or labels.shape[0] * 3 != logits.shape[0]:
+            raise ValueError(f"expected logits [3B, K] and labels [B], got {tuple(logits.shape)} and {tuple(labels.shape)}")
+        logits = logits.contiguous()
+        dev = nv.require_cuda(logits)
+        if not labels.is_cuda or labels.dtype != torch.int64:
+            raise nv.NativeError("labels must be an int64 CUDA tensor")
+        labels = labels.contiguous()
+        losses = torch.empty(3, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(logits)
+        with torch.cuda.device(dev):
+            rc = lib.dwt_head_loss_fwd_bwd(nv.ptr(logits), nv.ptr(labels), labels.shape[0], logits.shape[1], float(lam),
+                                           nv.ptr(losses), nv.ptr(grad), nv.stream_ptr(dev))
+        nv.check(rc)
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(losses)
+        return losses[0], losses
+
+    @staticmethod
+    def backward(ctx, g, _unused):
+        (grad,) = ctx.saved_tensors
+        return g * grad, None, None
+
+
+def head_loss(logits, labels, lambda_mec):
+    """-> (total loss (differentiable), tensor [total, classification, lambda*MEC])."""
+    return _HeadLossFunction.apply(logits, labels, lambda_mec)

@@ -140,6 +140,15 @@ DWT_API int dwt_mec_fwd_bwd(const float *x, const float *y, int64_t N, int64_t K
                     float *gy, dwt_stream_t stream);
 
 /*
+ * The whole head loss of one training step in one launch (resnet50_dwt_mec_officehome.py:421-428):
+ *   logits [3B, K] = source | target | target-aug, labels [B] (int64)
+ *   total = mean_n NLL(log_softmax(source_n), label_n) + lambda * MEC(target, target-aug)
+ * losses [3] = total, classification, lambda*MEC ;  grad [3B, K] = d total / d logits.
+ */
+DWT_API int dwt_head_loss_fwd_bwd(const float *logits, const int64_t *labels, int64_t B, int64_t K, float lambda,
+                          float *losses, float *grad, dwt_stream_t stream);
+
+/*
  * Measurement hooks (used by bench.py; not part of the reference's surface).
  * dwt_launch_count: kernels launched by this library since it was loaded.
  * dwt_profile_begin/end: while enabled, every kernel launch is bracketed by CUDA events on

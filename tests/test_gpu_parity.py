@@ -531,3 +531,25 @@ def test_fused_residual_tail_equals_unfused(kind, c, hw, gs, fmt, dev):
         res[mode] = [out.detach(), x.grad, r.grad, g.grad, b.grad]
     for a, bb in zip(res["fused"], res["unfused"]):
         assert rel_err(n(a), n(bb)) < 1e-5
+
+
+def test_head_loss_matches_reference_composition(dev):
+    """HeadLoss == nll_loss(log_softmax(source), y) + 0.1 * MinEntropyConsensusLoss(target, target_aug), value
+    and gradient of every logit row (oracle in fp64)."""
+    import dwt_b200
+    rng = np.random.default_rng(77)
+    B, K, lam = 64, 65, 0.1
+    z = 2.5 * rng.standard_normal((3 * B, K))
+    y = rng.integers(0, K, B)
+    zs = z[:B] - z[:B].max(1, keepdims=True)
+    lsm = zs - np.log(np.exp(zs).sum(1, keepdims=True))
+    cls = -lsm[np.arange(B), y].mean()
+    g_src = np.exp(lsm); g_src[np.arange(B), y] -= 1.0; g_src /= B
+    mec, gx, gy, _ = O.mec_loss(z[B:2 * B], z[2 * B:])
+    zt = t(z, dev).requires_grad_(True)
+    head = dwt_b200.HeadLoss(K, lam)
+    total = head(zt, torch.tensor(y, device=dev))
+    (1.7 * total).backward()
+    assert abs(total.item() - (cls + lam * mec)) < 1e-5 and abs(head.parts[1].item() - cls) < 1e-5
+    assert abs(head.parts[2].item() - lam * mec) < 1e-6
+    assert rel_err(n(zt.grad), 1.7 * np.concatenate([g_src, lam * gx, lam * gy])) < TOL_STAT
