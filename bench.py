@@ -411,10 +411,20 @@ def run_ours(args):
                     share_of_step=v["ms"] / ms_eager) for k, v in prof.items()}
     dom = max((k for k in fams if fams[k]["bytes"] > 0), key=lambda k: fams[k]["ms"], default=None)
     roof = None
+    traffic_tab = {}
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+    except Exception:
+        pass
     if dom is not None:
         f = fams[dom]
+        ratio = traffic_tab.get("traffic_over_algorithmic", {}).get(dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": f["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": f["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": f["gbs"] / peak,
+                # DRAM bytes per launch: this run's algorithmic bytes per launch x the traffic/algorithmic ratio of the
+                # committed `ncu --set full` capture of the same kernel (never measured under the profiler here)
+                "traffic": (ratio * f["bytes"] / f["launches"]) if ratio else None,
+                "traffic_source": traffic_tab.get("source") if ratio else None, "peak_source": peak_src,
                 "launches_timed": f["launches"], "avg_launch_us": f["us_per_launch"],
                 "algorithmic_bytes_per_launch": f["bytes"] / f["launches"],
                 "all_norm_kernels_share_of_step": sum(v["ms"] for v in fams.values()) / ms_eager,

@@ -13,13 +13,17 @@ SITES = [("whiten", 256, 56, 4), ("whiten", 64, 112, 4), ("whiten", 64, 56, 4), 
 def main():
     dev = torch.device("cuda", 0)
     which = [int(a) for a in sys.argv[1:] if a.isdigit()] or range(len(SITES))
+    cl = "cl" in sys.argv
     iters = 3
     res = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for i in which:
         kind, c, h, gs = SITES[i]
         n = 64
-        x = torch.randn(3 * n, c, h, h, device=dev).requires_grad_(True)
+        x = torch.randn(3 * n, c, h, h, device=dev)
+        if cl:
+            x = x.contiguous(memory_format=torch.channels_last)
+        x.requires_grad_(True)
         dout = torch.randn_like(x)
         if kind == "whiten":
             mods = [dwt_b200.WTransform2d(c, gs).to(dev).train() for _ in range(3)]
