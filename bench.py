@@ -304,7 +304,7 @@ def run_ours(args):
     nhwc = args.memory_format == "nhwc"
     model = build_model(dwt_b200, device, args.site_mode, channels_last=nhwc)
     net = model
-    sync = FlatGradAllReduce(model, world)
+    sync = FlatGradAllReduce(model, world) if distributed else None    # one GPU: plain autograd .grad tensors
     opt = make_optimizer(model)
     mec = dwt_b200.MinEntropyConsensusLoss(NUM_CLASSES, device)
     head = dwt_b200.HeadLoss(NUM_CLASSES, LAMBDA_MEC)

@@ -8,7 +8,7 @@ from harness.synth import synth_batch
 dev = torch.device("cuda", 0)
 torch.backends.cudnn.benchmark = True
 model = bench.build_model(dwt_b200, dev, "fused", channels_last=True)
-sync = bench.FlatGradAllReduce(model, 1)
+sync = None
 opt = bench.make_optimizer(model)
 head = dwt_b200.HeadLoss(65, 0.1)
 im, lb = synth_batch(3, 64)
