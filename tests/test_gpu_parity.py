@@ -553,3 +553,50 @@ def test_head_loss_matches_reference_composition(dev):
     assert abs(total.item() - (cls + lam * mec)) < 1e-5 and abs(head.parts[1].item() - cls) < 1e-5
     assert abs(head.parts[2].item() - lam * mec) < 1e-6
     assert rel_err(n(zt.grad), 1.7 * np.concatenate([g_src, lam * gx, lam * gy])) < TOL_STAT
+
+
+# --------------------------------------------------------------------------- edge cases
+def test_edge_shapes_and_inputs(dev):
+    """Single image per domain, a strided (non-dense) input view, a batch that does not split into the
+    domains, a half-precision tensor, an empty batch."""
+    import whitening
+    from dwt_b200 import DomainTripleNorm, _native
+    rng = np.random.default_rng(8)
+    # one image: statistics over H*W only
+    x = _correlated(rng, 1, 8, 9, 9)
+    y_o, *_ = O.whiten_forward(x, 4)
+    m = whitening.WTransform2d(8, 4).to(dev).train()
+    assert rel_err(n(m(t(x, dev))), y_o) < TOL
+    # a non-dense view (every second image of a larger batch): made dense internally, values unchanged
+    big = t(_correlated(rng, 8, 8, 6, 6), dev)
+    view = big[::2]
+    assert not view.is_contiguous()
+    y_o, *_ = O.whiten_forward(n(view), 4)
+    assert rel_err(n(whitening.WTransform2d(8, 4).to(dev).train()(view)), y_o) < TOL
+    # domain split must be exact
+    site = DomainTripleNorm("whiten", 8, 4)
+    mods = [whitening.WTransform2d(8, 4).to(dev).train() for _ in range(3)]
+    g, b = torch.ones(8, 1, 1, device=dev), torch.zeros(8, 1, 1, device=dev)
+    with pytest.raises(ValueError, match="does not split"):
+        site(torch.zeros(4, 8, 3, 3, device=dev), mods, g, b)
+    with pytest.raises(_native.NativeError, match="float32"):
+        whitening.WTransform2d(8, 4).to(dev)(torch.zeros(2, 8, 3, 3, device=dev, dtype=torch.float16))
+    with pytest.raises(_native.NativeError, match="empty tensor"):
+        whitening.WTransform2d(8, 4).to(dev)(torch.zeros(0, 8, 3, 3, device=dev))
+    with pytest.raises(_native.NativeError, match="group_size"):
+        whitening.WTransform2d(256, 128).to(dev)(torch.zeros(2, 256, 4, 4, device=dev))   # groups above 64 are not built
+
+
+def test_nonpositive_definite_sets_status_instead_of_syncing(dev):
+    """The reference raises from torch.cholesky (host sync).  Here a NaN input leaves NaN outputs and a device
+    status bit that the caller reads when it wants to."""
+    import whitening
+    from dwt_b200 import _native
+    x = torch.randn(4, 8, 5, 5, device=dev)
+    x[0, 0, 0, 0] = float("nan")
+    y = whitening.WTransform2d(8, 4).to(dev).train()(x)
+    assert torch.isnan(y[:, :4]).any() and not torch.isnan(y[:, 4:]).any()     # only the poisoned group
+    assert _native.status(dev) & 1
+    ws = _native._workspaces[(dev.index, torch.cuda.current_stream(dev).cuda_stream)]
+    ws[:4].zero_()                                                              # caller acknowledges
+    assert _native.status(dev) == 0
