@@ -121,12 +121,12 @@ ClPlan cl_plan(const dwt::Geom& g, int slots_per_sm) {
   const long long rows = (long long)g.N * g.HW;
   ClPlan p;
   p.gridy = gridy;
-  long long by_work = rows / ((long long)rpi * 64);
+  long long by_work = rows / ((long long)rpi * 16);      // >= 16 rows per thread (two load batches)
   if (by_work < 1) by_work = 1;
   int cap = slots_per_sm * sm_count() / (gridy * g.D);
   if (cap < 1) cap = 1;
   p.nred = (int)(by_work < cap ? by_work : cap);
-  long long by_work_ew = rows / ((long long)rpi * 32);
+  long long by_work_ew = rows / ((long long)rpi * 8);
   if (by_work_ew < 1) by_work_ew = 1;
   p.new_ = (int)(by_work_ew < 4LL * cap ? by_work_ew : 4LL * cap);
   p.S = p.nred < 8 ? p.nred : 8;
