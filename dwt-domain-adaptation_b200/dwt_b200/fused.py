@@ -11,6 +11,15 @@ sequential module calls.  Backward is likewise two launches and a
 dgamma/dbeta.
 
 It owns no state: it borrows the running buffers of the three domain modules at call time.
+
+``replicated=True`` is the statistics-collection pass (SURVEY.md §8f-3;
+resnet50_dwt_mec_officehome.py:380-389): the reference feeds ``cat((data, data, data))`` through
+the network in train mode under ``no_grad`` so that every domain branch folds the target batch
+into its running buffers.  The three thirds are identical, so are their statistics and their
+outputs: here x is the single copy [N, C, H, W], the statistics are computed once, the output is
+written once, and a buffer shared by k branches receives the k-fold EMA in one update,
+r <- (1-m)^k r + (1 - (1-m)^k) s -- a third of the traffic at every site and a third of the
+convolution work between them.
 """
 from __future__ import annotations
 
@@ -30,7 +39,7 @@ class DomainTripleNorm(nn.Module):
             raise NotImplementedError("the fused site is built for group sizes 1, 2 and 4 "
                                       f"(got {self.group_size}); use the per-domain modules")
 
-    def forward(self, x, domain_modules, gamma, beta, relu=False, residual=None):
+    def forward(self, x, domain_modules, gamma, beta, relu=False, residual=None, replicated=False):
         """x: [n_domains*N, C, H, W]; domain_modules: the per-domain WTransform2d / BatchNorm2d
         modules (training mode), whose buffers receive the EMA updates; gamma/beta: [C,1,1];
         residual (needs relu=True): out = relu(norm(x)*gamma + beta + residual), the Bottleneck tail
@@ -40,6 +49,8 @@ class DomainTripleNorm(nn.Module):
             raise ValueError(f"expected {self.n_domains} domain modules")
         if x.dim() != 4:
             raise ValueError('expected 4D input (got {}D input)'.format(x.dim()))
+        if replicated:
+            return self._forward_replicated(x, mods, gamma, beta, relu, residual)
         m0 = mods[0]
         if self.kind == "whiten":
             running = [(m.running_mean, m.running_variance) for m in mods]
@@ -55,3 +66,35 @@ class DomainTripleNorm(nn.Module):
         return F.norm(x, gamma, beta, kind=self.kind, group_size=self.group_size, n_domains=self.n_domains,
                       training_stats=True, eps=eps, momentum=momentum, update_running=update,
                       running=running, relu=relu, residual=residual)
+
+    def _forward_replicated(self, x, mods, gamma, beta, relu, residual):
+        """One copy of the batch stands for all n_domains branches (see the module docstring)."""
+        second = "running_variance" if self.kind == "whiten" else "running_var"
+        keep = {}                                  # distinct buffer pair -> product of (1 - factor) over its branches
+        for m in mods:
+            if not (m.training and m.track_running_stats):
+                continue
+            if self.kind == "bn":
+                m.num_batches_tracked += 1
+                f = m.momentum if m.momentum is not None else 1.0 / m.num_batches_tracked.item()
+            else:
+                f = m.momentum
+            rm, rv = m.running_mean, getattr(m, second)
+            key = (rm.data_ptr(), rv.data_ptr())
+            prod, _ = keep.get(key, (1.0, None))
+            keep[key] = (prod * (1.0 - f), (rm, rv))
+        means = {k[0] for k in keep}
+        seconds = {k[1] for k in keep}
+        if len(means) != len(keep) or len(seconds) != len(keep):
+            raise ValueError("replicated statistics need each running_mean paired with one second-moment buffer")
+        m0 = mods[0]
+        common = dict(kind=self.kind, group_size=self.group_size, n_domains=1, training_stats=True, eps=m0.eps,
+                      relu=relu, residual=residual)
+        if not keep:
+            return F.norm(x, gamma, beta, momentum=0.0, update_running=False,
+                          running=[(m0.running_mean, getattr(m0, second))], **common)
+        out = None
+        for prod, pair in keep.values():           # one launch per distinct buffer set (one, in a loaded model)
+            y = F.norm(x, gamma, beta, momentum=1.0 - prod, update_running=True, running=[pair], **common)
+            out = y if out is None else out
+        return out

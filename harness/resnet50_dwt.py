@@ -32,6 +32,9 @@ _DOMAINS = ("s", "t", "t_aug")                                   # bns*, bnt*, b
 EXPANSION = 4
 
 
+_REPLICATED = [False]          # set by collect_stats(): one copy of the batch stands for all three branches
+
+
 class WhitenScaleShift(nn.Module):
     """Same role and attribute names as the reference's ``whitening_scale_shift``
     (resnet50_dwt_mec_officehome.py:40-63): ``.wh`` is the whitening transform,
@@ -95,13 +98,16 @@ class _SiteOwner(nn.Module):
             fused = getattr(self, f"_fused_{tag}", None) if self.training else None
             if fused is not None:
                 mods = [getattr(self, n) for n in names]
-                return fused(x, [m.wh if whiten else m for m in mods], gamma, beta, True, residual=residual)
+                return fused(x, [m.wh if whiten else m for m in mods], gamma, beta, True, residual=residual,
+                             replicated=_REPLICATED[0])
             return torch.relu_(self._site(tag, x, relu=False) + residual)
         if self.training:
             fused = getattr(self, f"_fused_{tag}", None)
             mods = [getattr(self, n) for n in names]
             if fused is not None:
-                return fused(x, [m.wh if whiten else m for m in mods], gamma, beta, relu)
+                return fused(x, [m.wh if whiten else m for m in mods], gamma, beta, relu, replicated=_REPLICATED[0])
+            if _REPLICATED[0]:
+                raise RuntimeError("replicated statistics collection needs site_mode='fused'")
             parts = torch.split(x, x.shape[0] // 3, dim=0)
             s, t, a = (m(p) for m, p in zip(mods, parts))
             out = torch.cat((s, torch.cat((t, a), dim=0)), dim=0) * gamma + beta
@@ -182,3 +188,26 @@ def build_resnet50_dwt(state_dict, layers, site_mode="modules", num_classes=65, 
             if isinstance(m, nn.Conv2d):
                 m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
     return model
+
+
+def collect_stats(model, batches, passes=1, replicated=True):
+    """The reference's pre-evaluation pass (resnet50_dwt_mec_officehome.py:380-389): train-mode forwards
+    under no_grad that fold target batches into every branch's running statistics.  replicated=False is
+    the reference's own form, ``model(cat((data, data, data)))``; replicated=True (fused sites only) feeds
+    the single copy and lets each site apply the three identical updates at once."""
+    was_training = model.training
+    model.train(True)
+    out = None
+    try:
+        with torch.no_grad():
+            for _ in range(passes):
+                for data in batches:
+                    if replicated:
+                        _REPLICATED[0] = True
+                        out = model(data)
+                    else:
+                        out = model(torch.cat((data, data, data), dim=0))
+    finally:
+        _REPLICATED[0] = False
+        model.train(was_training)
+    return out

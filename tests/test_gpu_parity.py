@@ -600,3 +600,81 @@ def test_nonpositive_definite_sets_status_instead_of_syncing(dev):
     ws = _native._workspaces[(dev.index, torch.cuda.current_stream(dev).cuda_stream)]
     ws[:4].zero_()                                                              # caller acknowledges
     assert _native.status(dev) == 0
+
+
+# --------------------------------------------------------------------------- statistics-collection pass (§8f-3)
+@pytest.mark.parametrize("kind,owner", [("whiten", [0, 0, 0]), ("whiten", [0, 1, 1]), ("bn", [0, 0, 0]), ("bn", [0, 1, 2])])
+def test_replicated_site_equals_three_identical_domains(kind, owner, dev):
+    """resnet50_dwt_mec_officehome.py:380-389 feeds cat((d, d, d)); the replicated site takes d once and must
+    leave every branch's buffers where three sequential module calls on d leave them, with the same output."""
+    import batch_norm
+    import whitening
+    from dwt_b200 import DomainTripleNorm
+    rng = np.random.default_rng(31)
+    c, gs, nper, hw = 32, (4 if kind == "whiten" else 1), 4, 12
+    x = _correlated(rng, nper, c, hw, hw, offset=1.5)
+    rm0 = 0.1 * rng.standard_normal(c)
+    if kind == "whiten":
+        a = rng.standard_normal((c // gs, gs, gs))
+        rv0 = a @ a.transpose(0, 2, 1) / gs + 0.5 * np.eye(gs)
+    else:
+        rv0 = 0.5 + rng.random(c)
+    bufs = {o: [rm0.copy(), rv0.copy()] for o in set(owner)}
+    y_ref = None
+    for d in range(3):                                     # oracle: three sequential calls on the same data
+        if kind == "whiten":
+            y_ref, _, _, nrm, nrv, _ = O.whiten_forward(x, gs, running_mean=bufs[owner[d]][0], running_cov=bufs[owner[d]][1])
+        else:
+            y_ref, _, _, nrm, nrv = O.bn_forward(x, running_mean=bufs[owner[d]][0], running_var=bufs[owner[d]][1])
+        bufs[owner[d]] = [nrm, nrv]
+    if kind == "whiten":
+        tb = {o: (t(rm0.reshape(1, c, 1, 1), dev), t(rv0, dev)) for o in set(owner)}
+        mods = [whitening.WTransform2d(c, gs, running_m=tb[o][0], running_var=tb[o][1]).train() for o in owner]
+    else:
+        tb = {o: (t(rm0, dev), t(rv0, dev)) for o in set(owner)}
+        mods = [batch_norm.BatchNorm2d(c, tb[o][0], tb[o][1], affine=False).train() for o in owner]
+    g_t, b_t = torch.ones(c, 1, 1, device=dev), torch.zeros(c, 1, 1, device=dev)
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        for o in tb:
+            tb[o][0].copy_(t(rm0, dev).view_as(tb[o][0])); tb[o][1].copy_(t(rv0, dev))
+        with torch.no_grad():
+            y = DomainTripleNorm(kind, c, gs)(t(x, dev).contiguous(memory_format=fmt), mods, g_t, b_t, relu=False,
+                                              replicated=True)
+        assert y.shape[0] == nper and rel_err(n(y), y_ref) < TOL
+        for o in set(owner):
+            assert rel_err(n(tb[o][0]).reshape(-1), bufs[o][0].reshape(-1)) < TOL_STAT
+            assert rel_err(n(tb[o][1]), bufs[o][1]) < TOL_STAT
+    if kind == "bn":
+        assert all(int(m.num_batches_tracked) == 2 for m in mods)
+
+
+def test_collect_stats_replicated_matches_reference_form(dev):
+    """Whole model: the single-copy pass vs the reference's cat((d,d,d)) pass, the latter run both with the
+    CUDA layers and with the stock-ATen port of the reference layers."""
+    import dwt_b200
+    import oracle.torch_port as port
+    from harness.resnet50_dwt import build_resnet50_dwt, collect_stats
+    from harness.synth import synth_batch, synth_state_dict
+    x, _ = synth_batch(seed=5, per_domain=4, size=96)
+    batches = [x[:4].to(dev), x[4:8].to(dev)]
+
+    def fresh(layers, mode, cl=False):
+        sd = {k: v.to(dev) for k, v in synth_state_dict(seed=1).items()}
+        return build_resnet50_dwt(sd, layers, site_mode=mode, channels_last=cl).to(dev)
+
+    stock = fresh(port, "modules")
+    out_stock = collect_stats(stock, batches, passes=2, replicated=False)
+    triple = fresh(dwt_b200, "fused")
+    out_triple = collect_stats(triple, batches, passes=2, replicated=False)
+    single = fresh(dwt_b200, "fused", cl=True)
+    out_single = collect_stats(single, [b.contiguous(memory_format=torch.channels_last) for b in batches], passes=2)
+    assert out_single.shape[0] == 4 and out_triple.shape[0] == 12
+    assert rel_err(n(out_single), n(out_triple[:4])) < 1e-3 and rel_err(n(out_single), n(out_stock[4:8])) < 5e-3
+    b_stock, b_triple, b_single = stock.state_dict(), triple.state_dict(), single.state_dict()
+    for k, v in b_single.items():
+        if "running" in k:
+            assert rel_err(n(v), n(b_triple[k])) < 1e-3, k
+            assert rel_err(n(v), n(b_stock[k])) < 2e-3, k
+        elif k.endswith("num_batches_tracked"):
+            assert int(v) == int(b_stock[k]) == int(b_triple[k]), k
+    assert not single.training                               # collect_stats restores the caller's mode
