@@ -660,7 +660,7 @@ def test_collect_stats_replicated_matches_reference_form(dev):
 
     def fresh(layers, mode, cl=False):
         sd = {k: v.to(dev) for k, v in synth_state_dict(seed=1).items()}
-        return build_resnet50_dwt(sd, layers, site_mode=mode, channels_last=cl).to(dev)
+        return build_resnet50_dwt(sd, layers, site_mode=mode, channels_last=cl).to(dev).eval()
 
     stock = fresh(port, "modules")
     out_stock = collect_stats(stock, batches, passes=2, replicated=False)
