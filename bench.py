@@ -84,6 +84,11 @@ class ClockSampler:
                                           "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi's start-up (NVML init, driver queries) briefly stalls launches on the GPU it opens: let
+            # it deliver its first sample before the timed region starts
+            t_end = time.time() + 5.0
+            while not self.rows and time.time() < t_end:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
         return self
@@ -463,10 +468,22 @@ def run_microbench(args, device, rank):
 
     for _ in range(args.warmup):
         step()
+    graph = None
+    if args.cuda_graph:                              # the four launches as one graph: no host time between them
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream(device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        graph.replay()
     with ClockSampler(device.index) as clocks:
         _native.profile_begin()
-        ms = timed_loop(step, args.steps, device, False)
+        eager_ms = timed_loop(step, args.steps, device, False)
         prof = _native.by_family(_native.profile_end())
+        ms = timed_loop(graph.replay, args.steps, device, False) if graph is not None else eager_ms
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
@@ -478,9 +495,11 @@ def run_microbench(args, device, rank):
     print(json.dumps({
         "metric": "WTransform2d fwd+bwd microbench", "value": args.steps / (ms * 1e-3), "unit": "iterations/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "eager_ms_per_step": eager_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"WTransform2d N={N} C={C} H=W={H} group_size={gs} fwd+bwd",
-                   "l2": f"tensor of {elems * 4 / 1e6:.0f} MB > 126 MB L2"},
+                   "l2": f"tensor of {elems * 4 / 1e6:.0f} MB > 126 MB L2",
+                   "launch": "cuda-graph replay" if graph is not None else "eager"},
         "roofline": {"bound": "hbm", "kernel": "fwd+bwd (4 launches)", "achieved": gbs, "peak": peak, "unit": "GB/s",
                      "frac": gbs / peak, "traffic": None, "peak_source": peak_src},
         "kernels": fams, "clocks": clocks.summary(),

@@ -106,10 +106,10 @@ int tc_chunks(const dwt::Geom& g) {
 }
 
 // persistent CTAs per (domain, super-block) of the tensor-core apply kernels: per_sm CTAs per SM
-int tc_apply_ctas(const dwt::Geom& g, int per_sm) {
+int tc_apply_ctas(const dwt::Geom& g, int per_sm, int tile_px) {
   const int problems = dwt::tc_superblocks(g) * g.D;
   int n = per_sm * sm_count() / problems;
-  const int64_t tiles = (int64_t)g.N * ((g.HW + 63) / 64);
+  const int64_t tiles = (int64_t)g.N * ((g.HW + tile_px - 1) / tile_px);
   if (n > tiles) n = (int)tiles;
   return n < 1 ? 1 : n;
 }
@@ -364,7 +364,7 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
     Launch l(p.small ? "small_apply" : (tc ? "tc_apply" : "tiled_apply"), &p.gm, ((epi & DWT_EPI_RESIDUAL) ? 3 : 2) * E, st);
     if (p.small) dwt::small_apply(x, y, p.gm_ew, p.vec, p.chunks_ew, epi, save_mean, save_w, gamma, beta, residual, st);
     else if (tc) {
-      if (int cr = dwt::tc_apply(x, y, p.gm, tc_apply_ctas(p.gm, 2), save_mean, save_w, st))
+      if (int cr = dwt::tc_apply(x, y, p.gm, tc_apply_ctas(p.gm, 2, 64), save_mean, save_w, st))
         return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed (CUresult %d)", cr);
     } else dwt::tiled_apply(x, y, p.gm_ew, p.vec, p.chunks_ew, save_mean, save_w, st);
   }
@@ -452,7 +452,7 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
     Launch l(p.small ? "small_bwd_apply" : (tc ? "tc_bwd_apply" : "tiled_bwd_apply"), &p.gm, 3 * E, st);
     if (p.small) dwt::small_bwd_apply(x, dout, dx, p.gm_ew, p.vec, p.chunks_ew, epi, w.coef, save_mean, save_w, gamma, beta, st);
     else if (tc) {
-      if (int cr = dwt::tc_bwd_apply(x, dout, dx, p.gm, tc_apply_ctas(p.gm, 1), w.coef, save_mean, w.shift, st))
+      if (int cr = dwt::tc_bwd_apply(x, dout, dx, p.gm, tc_apply_ctas(p.gm, 1, 128), w.coef, save_mean, w.shift, st))
         return fail(DWT_E_LAUNCH, "cuTensorMapEncodeTiled failed (CUresult %d)", cr);
     } else dwt::tiled_bwd_apply(x, dout, dx, p.gm_ew, p.vec, p.chunks_ew, w.coef, st);
   }

@@ -4,6 +4,14 @@
 
 namespace dwt {
 
+// The driver-API tensor-map encoder needs a current context and autograd worker threads arrive without one.
+// cudaFree(0) binds the primary context but is illegal inside a stream capture: do it once per thread (the
+// first call of a thread is a warm-up call, never a captured one).
+inline void bind_context() {
+  thread_local bool bound = false;
+  if (!bound) { cudaFree(nullptr); bound = true; }
+}
+
 // register-resident path, GS in {1,2,4}  (norm_small.cu)
 bool small_supports(int GS);
 void small_stats(const float* x, const Geom& gm, int vec, const FwdFin& fin, float* partial, int* counters,

@@ -281,7 +281,7 @@ int tc_superblocks(const Geom& gm) { return (gm.C + kTileCh - 1) / kTileCh; }
 // partial: [D][SB][nchunks][64*64+64] per-CTA moments;  shift: [D][SB][64] pilot shift of every channel
 int tc_stats(const float* x, const Geom& gm, int nchunks, float* shift, float* partial, cudaStream_t st) {
   CUtensorMap mx;
-  cudaFree(nullptr);        // bind the primary context to this thread (autograd workers call in cold)
+  bind_context();
   if (int rc = make_map(&mx, x, gm)) return rc;
   dim3 grid(nchunks, tc_superblocks(gm), gm.D);
   tc_contract_kernel<false><<<grid, kTcThreads, tc_smem_bytes(false), st>>>(mx, mx, x, gm, nullptr, shift, partial);
@@ -291,7 +291,7 @@ int tc_stats(const float* x, const Geom& gm, int nchunks, float* shift, float* p
 int tc_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nchunks, const float* save_mean,
                   float* partial, cudaStream_t st) {
   CUtensorMap mx, mg;
-  cudaFree(nullptr);
+  bind_context();
   if (int rc = make_map(&mx, x, gm)) return rc;
   if (int rc = make_map(&mg, dout, gm)) return rc;
   dim3 grid(nchunks, tc_superblocks(gm), gm.D);

@@ -5,20 +5,32 @@
 //
 // Per 64-channel super-block the per-group matrices form one block-diagonal 64x64 matrix M, and a
 // [64 ch x 64 px] tile of the NCHW tensor is out = M * tile: a GEMM whose B operand is the tile exactly
-// as TMA lands it (rows = channels = K, pixels contiguous = MN-major), so again nothing is transposed.
+// as TMA lands it (rows = channels = K, pixels contiguous = MN-major), so nothing is transposed.
 // A single-pass TF32 product is NOT accurate enough here -- each output is one length-64 dot product
 // whose terms can cancel by the condition number of the covariance -- so both operands are split
-// x = hi + lo (hi = RN_tf32(x), lo = RN_tf32(x - hi)) and the four partial products are accumulated in
-// fp32: the matrix halves are STACKED as a 128-row A operand [M_hi ; M_lo], so one M=128 MMA per B half
-// yields M_hi*B and M_lo*B rows in TMEM; the epilogue adds the two row halves.
+// x = hi + lo and the four partial products are accumulated in fp32:
+//   matrix  hi = RN_tf32(m), lo = RN_tf32(m - hi), STACKED as a 128-row A operand [M_hi ; M_lo]: one M=128 MMA
+//           per B half yields M_hi*B and M_lo*B rows in TMEM and the epilogue adds the two row halves;
+//   tile    hi = the landed fp32 words themselves (the tensor core reads the top 19 bits: trunc_tf32), so the
+//           raw tile is an operand as it is; lo = RN_tf32(x - trunc_tf32(x)) is the only thing computed and
+//           written per element;
+//   centring is linear, M (x - shift) = M x - M shift, and is applied as one constant per row at the end.
 //
-// CTA = 10 warps, persistent over a contiguous range of 64-pixel tiles of one (domain, super-block):
-//   warp 0     TMA producer (2 boxes of 32 px x 64 ch per input tensor and stage, SWIZZLE_128B_ATOM_32B:
-//              the only layout the tensor core takes for an MN-major tf32 operand)
+// CTA = 2 + 4 + 4 warps (one input, two CTAs per SM) or 2 + 8 + 8 warps (two inputs, one CTA per SM), persistent over a contiguous range of 64-pixel tiles of one (domain, super-block):
+//   warp 0     TMA producer into a RAW ring (2 boxes of 32 px x 64 ch per input tensor and slot,
+//              SWIZZLE_128B_ATOM_32B: the only layout the tensor core takes for an MN-major tf32 operand)
 //   warp 1     MMA issuer (tcgen05.mma kind::tf32, M=128 N=64 K=8; A resident in TMEM, B MN-major), TMEM owner
-//   warps 2-5  transform: in place hi = RN(v - shift[c]), second buffer lo = RN(v - shift[c] - hi)
-//   warps 6-9  epilogue: tcgen05.ld 128 lanes x 64 columns, fold the hi/lo row halves with one shuffle,
-//              256-byte row stores; TMEM accumulators are double-buffered against the MMA.
+//   TW warps   transform: raw slot -> lo slot
+//   EW warps   epilogue: tcgen05.ld of this warp's lane quadrant x (64 or 32) columns, hi/lo row halves folded
+//              by a half-warp exchange in which each half keeps half of the columns, 256-bit stores.
+//              (One merged worker group doing transform(it) then epilogue(it-1) serialised transform -> MMA ->
+//              epilogue into one chain: 1.5 us per two-input tile against 0.6 us of tensor time.)
+// The raw ring is deeper than the lo ring: a raw slot is busy from the TMA issue to the end of its MMAs (one HBM
+// latency + transform + MMA), a lo slot only from the transform to the end of the MMAs, and the bytes in flight
+// from HBM -- what bounds this kernel -- are the raw slots alone.  TMEM accumulators are double-buffered.
+//
+// Measured ceilings on B200 (N=256, C=256, 56x56, profiles/tc_apply_experiments_r01.md): TMA loads alone 0.96 of
+// the HBM peak; a pure TMA load->store copy in this tile order 0.88-0.91.
 //
 // Reference: the grouped 1x1 convolution at utils/whitening.py:55 (/root/reference) and its backward.
 #include <cuda.h>
@@ -32,17 +44,32 @@ namespace {
 
 using namespace tc;
 
-constexpr int kApThreads = 320;
-constexpr int kBoxPx = 32, kTilePxA = 64, kCh = 64;
+constexpr int kBoxPx = 32, kCh = 64;
 constexpr int kBoxBytes = kCh * kBoxPx * 4;          // 8192
-constexpr int kHalfBytes = 2 * kBoxBytes;            // hi (or lo) of one input: 2 boxes = 16 KB
-constexpr int kInBytes = 2 * kHalfBytes;             // hi + lo of one input = 32 KB
-constexpr int kAccCols = 64;                         // TMEM columns per accumulator / per matrix
-constexpr int kTmemAlloc = 256;                      // 2 accumulators + up to 2 resident matrices
-constexpr int kMaxStages = 4;
+constexpr int kMatCols = 64;                         // TMEM columns per resident matrix
+constexpr int kMaxRaw = 6, kLo = 2;
+
+// One STEP = one input tensor's [64 ch x TPX px] tile: a raw ring slot filled by TMA, a lo ring slot filled by the
+// transform warps, 16 MMAs (2 terms x 8 k-steps of N = TPX) accumulating into the tile's TMEM accumulator.
+// The issue cost of a tcgen05.mma is ~90 cycles whatever its N (measured: one warp issuing 32 N=64 MMAs per
+// two-input tile was 90 % busy with the tensor pipe 35 % active), so the two-input kernel uses N = 128:
+//   one input : TPX  64, 4 raw + 2 lo slots of 16 KB =  97 KB, 2 + 4 + 4 warps, two CTAs per SM, 256 TMEM columns
+//   two inputs: TPX 128, 5 raw + 2 lo slots of 32 KB = 225 KB, 2 + 8 + 8 warps, one CTA per SM,  512 TMEM columns
+template <int NIN> struct ApCfg {
+  static constexpr int TPX = NIN == 1 ? 64 : 128;
+  static constexpr int NBOX = TPX / kBoxPx;
+  static constexpr int TW = NIN == 1 ? 4 : 8;          // transform warps
+  static constexpr int EW = NIN == 1 ? 4 : 8;          // epilogue warps (per SM: 8 + 8 either way)
+  static constexpr int THREADS = 64 + 32 * (TW + EW);
+  static constexpr int RAW = NIN == 1 ? 4 : 5;
+  static constexpr int SLOT = NBOX * kBoxBytes;
+  static constexpr int TMEM = NIN == 1 ? 256 : 512;    // 2 accumulators of TPX columns + NIN matrices of 64
+  static constexpr size_t SMEM = (size_t)(RAW + kLo) * SLOT + 1024;
+};
 
 struct ApBarriers {
-  uint64_t full[kMaxStages], ready[kMaxStages], empty[kMaxStages];
+  uint64_t full[kMaxRaw], raw_empty[kMaxRaw];       // TMA landed / MMAs done with the raw slot
+  uint64_t ready[kLo], lo_empty[kLo];               // lo slot written / MMAs done with it
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_slot;
 };
@@ -56,17 +83,32 @@ struct ApplyArgs {
   float* out;
 };
 
-// hi/lo split of one landed 32 px x 64 ch box by the 128 transform threads (tt = 0..127).
-__device__ __forceinline__ void split_box(float* hi, float* lo, int tt, const float (&shift)[4]) {
+// 128-bit shared-memory accesses with the state space spelled out: through a generic pointer these compile to
+// LD.E/ST.E (address-space check per access, global-load latency class); LDS/STS is what the transform wants.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// lo = RN_tf32(v - trunc_tf32(v)) (the subtraction is exact) of one landed 32 px x 64 ch box by the 256 worker
+// threads (tt = 0..NT-1): chunk q = tt + NT i (16 bytes), same swizzled position in the lo slot.
+template <int NT>
+__device__ __forceinline__ void lo_box(uint32_t raw, uint32_t lo, int tt) {
+  constexpr int PER = 512 / NT;
+  float4 v[PER];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int q = tt + 128 * i;                    // 16-byte chunk; row = q >> 3
-    float4 v = reinterpret_cast<float4*>(hi)[q];
-    float e[4] = {v.x - shift[i], v.y - shift[i], v.z - shift[i], v.w - shift[i]}, h[4], l[4];
+  for (int i = 0; i < PER; ++i) v[i] = lds128(raw + 16u * (tt + NT * i));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { h[k] = round_tf32(e[k]); l[k] = round_tf32(e[k] - h[k]); }
-    reinterpret_cast<float4*>(hi)[q] = make_float4(h[0], h[1], h[2], h[3]);
-    reinterpret_cast<float4*>(lo)[q] = make_float4(l[0], l[1], l[2], l[3]);
+  for (int i = 0; i < PER; ++i) {
+    const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    float l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) l[k] = round_tf32(e[k] - __uint_as_float(__float_as_uint(e[k]) & 0xFFFFE000u));
+    sts128(lo + 16u * (tt + NT * i), l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -76,27 +118,31 @@ __device__ __forceinline__ void split_box(float* hi, float* lo, int tt, const fl
 // for l >= 16, so the two halves that must be added end up 16 lanes apart IN THE SAME WARP and the
 // epilogue folds them with one shuffle per value -- no shared-memory staging at all.
 template <int NIN>
-__global__ void __launch_bounds__(kApThreads, NIN == 1 ? 2 : 1)
+__global__ void __launch_bounds__(ApCfg<NIN>::THREADS, NIN == 1 ? 2 : 1)
 tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Geom gm,
                 const ApplyArgs args) {
-  constexpr int STAGES = 3;       // NIN = 1: 97 KB -> two CTAs per SM; NIN = 2: 193 KB -> one
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  using Cfg = ApCfg<NIN>;
+  constexpr int RAW = Cfg::RAW, SLOT = Cfg::SLOT, TW = Cfg::TW, EW = Cfg::EW, TPX = Cfg::TPX, NBOX = Cfg::NBOX;
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* sRaw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sLo = sRaw + (size_t)RAW * SLOT;
   __shared__ ApBarriers bars;
   __shared__ float sShift[2][kCh];
+  __shared__ float sConst[kCh];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int sb = blockIdx.y, d = blockIdx.z, ch0 = sb * kCh;
-  const int PB = (gm.HW + kTilePxA - 1) / kTilePxA;
+  const int PB = (gm.HW + TPX - 1) / TPX;
   const long long T = (long long)gm.N * PB;
   const int t_begin = (int)(T * blockIdx.x / gridDim.x), t_end = (int)(T * (blockIdx.x + 1) / gridDim.x);
   const int ntiles = t_end - t_begin;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.ready[s], 4); mbar_init(&bars.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_empty[b], 4); }
+    for (int r = 0; r < RAW; ++r) { mbar_init(&bars.full[r], 1); mbar_init(&bars.raw_empty[r], 1); }
+    for (int l = 0; l < kLo; ++l) { mbar_init(&bars.ready[l], TW); mbar_init(&bars.lo_empty[l], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_empty[b], EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<kTmemAlloc>(&bars.tmem_slot);
+  if (warp == 1) tmem_alloc<Cfg::TMEM>(&bars.tmem_slot);
   if (tid < NIN * kCh) {
     const int i = tid / kCh, r = tid - i * kCh, c = ch0 + r;
     sShift[i][r] = (c < gm.C && args.shift[i] != nullptr) ? __ldg(args.shift[i] + (size_t)d * args.shift_stride[i] + c) : 0.f;
@@ -105,12 +151,13 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_slot;
-  const uint32_t tmem_acc = tmem, tmem_mat = tmem + 2 * kAccCols;
+  const uint32_t tmem_acc = tmem, tmem_mat = tmem + 2 * TPX;
 
-  if (warp >= 6) {
-    // epilogue warps first park the split matrices in tensor memory
+  if (warp >= 2 + TW && warp < 6 + TW) {
+    // four of the epilogue warps first park the split matrices in tensor memory and form the row constants
     const int quad = warp & 3, i = 16 * quad + (lane & 15), GS = gm.GS, gi = i / GS, g = sb * (kCh / GS) + gi;
     const bool lo_half = lane >= 16;
+    float rc = 0.f;                       // (sum_m M_m shift_m)[row i], full fp32 matrix entries
     for (int m = 0; m < NIN; ++m) {
       const float* rec = args.mats + ((size_t)d * gm.G + (g < gm.G ? g : 0)) * args.rec_stride + args.off[m] + (i - gi * GS) * GS;
 #pragma unroll
@@ -121,12 +168,14 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
           const int k = h * 32 + c;
           float w = 0.f;
           if (g < gm.G && k / GS == gi) w = __ldg(rec + (k - gi * GS));
+          rc = fmaf(w, sShift[m][k], rc);
           const float hi = round_tf32(w);
           v[c] = lo_half ? round_tf32(w - hi) : hi;
         }
-        tmem_st32(tmem_mat + m * kAccCols + ((uint32_t)(quad * 32) << 16) + h * 32, v);
+        tmem_st32(tmem_mat + m * kMatCols + ((uint32_t)(quad * 32) << 16) + h * 32, v);
       }
     }
+    if (!lo_half) sConst[i] = rc;
     tc_fence_before();
   }
   __syncthreads();
@@ -136,119 +185,119 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     // ===== TMA producer =====
     if (lane == 0) {
       for (int it = 0; it < ntiles; ++it) {
-        const int s = it % STAGES, ph = (it / STAGES) & 1;
-        mbar_wait(&bars.empty[s], ph ^ 1);
         const int t = t_begin + it, n = t / PB, pb = t - n * PB;
-        uint8_t* dst = sStage + (size_t)s * NIN * kInBytes;
-        // the second 32-pixel box of the tile may lie entirely past the row end: do not issue it (its
-        // columns are never stored, whatever the stale shared memory holds)
-        const int nbox = (pb * kTilePxA + kBoxPx < gm.HW) ? 2 : 1;
-        mbar_arrive_expect_tx(&bars.full[s], NIN * nbox * kBoxBytes);
+        // 32-pixel boxes of the tile that lie entirely past the row end are not issued (their columns are never
+        // stored, whatever the stale shared memory holds)
+        int nbox = (gm.HW - pb * TPX + kBoxPx - 1) / kBoxPx;
+        nbox = nbox < NBOX ? nbox : NBOX;
 #pragma unroll
-        for (int i = 0; i < NIN; ++i)
+        for (int i = 0; i < NIN; ++i) {
+          const int st = it * NIN + i, r = st % RAW;
+          mbar_wait(&bars.raw_empty[r], ((st / RAW) & 1) ^ 1);
+          uint8_t* dst = sRaw + (size_t)r * SLOT;
+          mbar_arrive_expect_tx(&bars.full[r], nbox * kBoxBytes);
           for (int j = 0; j < nbox; ++j)
-            tma_load_3d(dst + i * kInBytes + j * kBoxBytes, i == 0 ? &map0 : &map1, pb * kTilePxA + j * kBoxPx, ch0,
-                        d * gm.N + n, &bars.full[s]);
+            tma_load_3d(dst + j * kBoxBytes, i == 0 ? &map0 : &map1, pb * TPX + j * kBoxPx, ch0, d * gm.N + n, &bars.full[r]);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc_tf32(128, kTilePxA, true);
+    constexpr uint32_t idesc = make_idesc_tf32(128, TPX, true);
     for (int it = 0; it < ntiles; ++it) {
-      const int s = it % STAGES, ph = (it / STAGES) & 1, b = it & 1, aph = (it >> 1) & 1;
-      mbar_wait(&bars.ready[s], ph);
+      const int b = it & 1, aph = (it >> 1) & 1;
       mbar_wait(&bars.acc_empty[b], aph ^ 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t stage = smem_u32(sStage + (size_t)s * NIN * kInBytes);
-        uint32_t first = 1;
 #pragma unroll
-        for (int i = 0; i < NIN; ++i) {
+      for (int i = 0; i < NIN; ++i) {
+        const int st = it * NIN + i, r = st % RAW, l = st % kLo;
+        mbar_wait(&bars.full[r], (st / RAW) & 1);             // already complete (the transform warps waited on it)
+        mbar_wait(&bars.ready[l], (st / kLo) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t raw = smem_u32(sRaw + (size_t)r * SLOT), lo = smem_u32(sLo + (size_t)l * SLOT);
 #pragma unroll
-          for (int term = 0; term < 2; ++term) {                 // B = hi half, then lo half
-            const uint32_t bbase = stage + i * kInBytes + term * kHalfBytes;
+          for (int term = 0; term < 2; ++term) {                 // B = raw tile (hi by truncation), then lo
+            const uint32_t bbase = term == 0 ? raw : lo;
 #pragma unroll
             for (int ks = 0; ks < kCh / 8; ++ks) {
               const uint64_t bdesc = make_mnmajor_sw128_32b_desc(bbase + ks * 1024, kBoxBytes, 512);
-              umma_tf32_ts(tmem_acc + b * kAccCols, tmem_mat + i * kAccCols + ks * 8, bdesc, idesc, first ? 0u : 1u);
-              first = 0;
+              umma_tf32_ts(tmem_acc + b * TPX, tmem_mat + i * kMatCols + ks * 8, bdesc, idesc,
+                           (i == 0 && term == 0 && ks == 0) ? 0u : 1u);
             }
           }
+          umma_commit(&bars.raw_empty[r]);
+          umma_commit(&bars.lo_empty[l]);
+          if (i == NIN - 1) umma_commit(&bars.acc_full[b]);
         }
-        umma_commit(&bars.empty[s]);
-        umma_commit(&bars.acc_full[b]);
+        __syncwarp();
       }
-      __syncwarp();
     }
-  } else if (warp < 6) {
-    // ===== transform warps =====
+  } else if (warp < 2 + TW) {
+    // ===== transform warps: raw slot -> lo slot, one step at a time =====
     const int tt = tid - 64;
-    float sh[2][4];
+    const uint32_t raw0 = smem_u32(sRaw), lo0 = smem_u32(sLo);
+    for (int st = 0; st < ntiles * NIN; ++st) {
+      const int r = st % RAW, l = st % kLo;
+      mbar_wait(&bars.full[r], (st / RAW) & 1);
+      mbar_wait(&bars.lo_empty[l], ((st / kLo) & 1) ^ 1);
+      const uint32_t raw = raw0 + (uint32_t)(r * SLOT), lo = lo0 + (uint32_t)(l * SLOT);
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int r = 0; r < 4; ++r) sh[i][r] = sShift[i][(tt + 128 * r) >> 3];
-    for (int it = 0; it < ntiles; ++it) {
-      const int s = it % STAGES, ph = (it / STAGES) & 1;
-      mbar_wait(&bars.full[s], ph);
-      uint8_t* st = sStage + (size_t)s * NIN * kInBytes;
-#pragma unroll
-      for (int i = 0; i < NIN; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          split_box(reinterpret_cast<float*>(st + i * kInBytes + j * kBoxBytes),
-                    reinterpret_cast<float*>(st + i * kInBytes + kHalfBytes + j * kBoxBytes), tt, sh[i]);
+      for (int j = 0; j < NBOX; ++j) lo_box<32 * TW>(raw + j * kBoxBytes, lo + j * kBoxBytes, tt);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.ready[s]);
+      if (lane == 0) mbar_arrive(&bars.ready[l]);
     }
   } else {
     // ===== epilogue warps =====
-    const int quad = warp & 3;                     // TMEM lane quadrant of this warp
-    const int ch = ch0 + 16 * quad + (lane & 15);  // channel whose hi (lane<16) / lo (lane>=16) row this thread reads
-    for (int it = 0; it < ntiles; ++it) {
-      const int b = it & 1, aph = (it >> 1) & 1;
+    constexpr int WC = TPX / (EW / 4), KEEP = WC / 2;  // accumulator columns per warp / per lane after the fold
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may read
+    const int part = (warp - 2 - TW) >> 2;         // which WC accumulator columns this warp drains
+    const bool upper = lane >= 16;                 // lanes 16-31 hold the lo-matrix rows
+    const int ch = ch0 + 16 * quad + (lane & 15);
+    const float rconst = sConst[16 * quad + (lane & 15)];   // sum_i (M_i shift_i)[row]: the centring, applied at the end
+    for (int e = 0; e < ntiles; ++e) {
+      const int b = e & 1, aph = (e >> 1) & 1;
       mbar_wait(&bars.acc_full[b], aph);
       tc_fence_after();
-      float v[2][32];
-      tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + b * kAccCols, v[0]);
-      tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + b * kAccCols + 32, v[1]);
+      float v[WC];
+      tmem_ld_cols<WC>(tmem_acc + ((uint32_t)(quad * 32) << 16) + b * TPX + part * WC, v);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.acc_empty[b]);          // accumulator drained: MMA may reuse it
+      if (lane == 0) mbar_arrive(&bars.acc_empty[b]);          // this warp's share is drained
+      // lanes l and l+16 hold the hi- and lo-matrix rows of one channel: the lower lane keeps the first half of
+      // the summed columns, the upper lane the second half, each sending the other the values it does not keep
+      float o[KEEP];
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int c = 0; c < 32; ++c) v[h][c] += __shfl_down_sync(0xffffffffu, v[h][c], 16);
-      const int t = t_begin + it, n = t / PB, pb = t - n * PB, px0 = pb * kTilePxA;
-      if (lane < 16 && ch < gm.C) {
-        float* orow = args.out + ((size_t)(d * gm.N + n) * gm.C + ch) * gm.HW + px0;
+      for (int c = 0; c < KEEP; ++c) {
+        const float keep = upper ? v[KEEP + c] : v[c];
+        const float send = upper ? v[c] : v[KEEP + c];
+        o[c] = (keep + __shfl_xor_sync(0xffffffffu, send, 16)) - rconst;
+      }
+      const int t = t_begin + e, n = t / PB, pb = t - n * PB;
+      const int px = pb * TPX + part * WC + (upper ? KEEP : 0);
+      if (ch < gm.C) {
+        float* orow = args.out + ((size_t)(d * gm.N + n) * gm.C + ch) * gm.HW + px;
         if ((gm.HW & 7) == 0) {
-          // 256-bit stores (sm_100 STG.256): every instruction writes whole 32-byte sectors of this thread's row;
-          // 128-bit stores left half-written sectors behind (16 sectors per request, 2x the L2 write traffic)
+          // 256-bit stores (sm_100 STG.256): every instruction writes whole 32-byte sectors of this lane's row;
+          // 128-bit stores left half-written sectors behind (2x the L2 write traffic)
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8)
-              if (px0 + h * 32 + 8 * c8 < gm.HW)
-                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + h * 32 + 8 * c8),
-                             "f"(v[h][8 * c8]), "f"(v[h][8 * c8 + 1]), "f"(v[h][8 * c8 + 2]), "f"(v[h][8 * c8 + 3]),
-                             "f"(v[h][8 * c8 + 4]), "f"(v[h][8 * c8 + 5]), "f"(v[h][8 * c8 + 6]), "f"(v[h][8 * c8 + 7]) : "memory");
+          for (int c8 = 0; c8 < KEEP / 8; ++c8)
+            if (px + 8 * c8 < gm.HW)
+              asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + 8 * c8),
+                           "f"(o[8 * c8]), "f"(o[8 * c8 + 1]), "f"(o[8 * c8 + 2]), "f"(o[8 * c8 + 3]),
+                           "f"(o[8 * c8 + 4]), "f"(o[8 * c8 + 5]), "f"(o[8 * c8 + 6]), "f"(o[8 * c8 + 7]) : "memory");
         } else {
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4)
-              if (px0 + h * 32 + 4 * c4 < gm.HW)
-                *reinterpret_cast<float4*>(orow + h * 32 + 4 * c4) =
-                    make_float4(v[h][4 * c4], v[h][4 * c4 + 1], v[h][4 * c4 + 2], v[h][4 * c4 + 3]);
+          for (int c4 = 0; c4 < KEEP / 4; ++c4)
+            if (px + 4 * c4 < gm.HW)
+              *reinterpret_cast<float4*>(orow + 4 * c4) = make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc<kTmemAlloc>(tmem); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<ApCfg<NIN>::TMEM>(tmem); }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -266,7 +315,7 @@ int make_map_ap(CUtensorMap* map, const float* base, const Geom& gm) {
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-template <int NIN> constexpr size_t ap_smem() { return (size_t)3 * NIN * kInBytes + 1024; }
+template <int NIN> constexpr size_t ap_smem() { return ApCfg<NIN>::SMEM; }
 
 }  // namespace
 
@@ -278,7 +327,7 @@ int tc_apply_init() {
   g_encode_ap = reinterpret_cast<EncodeTiledFn>(fn);
   e = cudaFuncSetAttribute(tc_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ap_smem<1>());
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ap_smem<2>());
-  // two 97 KB CTAs per SM need the full shared-memory carve-out
+  // two 97 KB CTAs (or one 225 KB CTA) per SM need the full shared-memory carve-out
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_apply_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_apply_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   return (int)e;
@@ -288,14 +337,14 @@ int tc_apply_init() {
 int tc_apply(const float* x, float* y, const Geom& gm, int nctas, const float* save_mean, const float* save_w,
              cudaStream_t st) {
   CUtensorMap mx;
-  cudaFree(nullptr);
+  bind_context();
   if (int rc = make_map_ap(&mx, x, gm)) return rc;
   ApplyArgs a{};
   a.mats = save_w; a.rec_stride = gm.GS * gm.GS; a.off[0] = 0; a.off[1] = 0;
   a.shift[0] = save_mean; a.shift_stride[0] = gm.C; a.shift[1] = nullptr; a.shift_stride[1] = 0;
   a.out = y;
   dim3 grid(nctas, (gm.C + kCh - 1) / kCh, gm.D);
-  tc_apply_kernel<1><<<grid, kApThreads, ap_smem<1>(), st>>>(mx, mx, gm, a);
+  tc_apply_kernel<1><<<grid, ApCfg<1>::THREADS, ap_smem<1>(), st>>>(mx, mx, gm, a);
   return 0;
 }
 
@@ -303,7 +352,7 @@ int tc_apply(const float* x, float* y, const Geom& gm, int nctas, const float* s
 int tc_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, const float* coef,
                  const float* save_mean, const float* dybar, cudaStream_t st) {
   CUtensorMap mx, mg;
-  cudaFree(nullptr);
+  bind_context();
   if (int rc = make_map_ap(&mg, dout, gm)) return rc;
   if (int rc = make_map_ap(&mx, x, gm)) return rc;
   ApplyArgs a{};
@@ -312,7 +361,7 @@ int tc_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, i
   a.shift[1] = save_mean; a.shift_stride[1] = gm.C;
   a.out = dx;
   dim3 grid(nctas, (gm.C + kCh - 1) / kCh, gm.D);
-  tc_apply_kernel<2><<<grid, kApThreads, ap_smem<2>(), st>>>(mg, mx, gm, a);
+  tc_apply_kernel<2><<<grid, ApCfg<2>::THREADS, ap_smem<2>(), st>>>(mg, mx, gm, a);
   return 0;
 }
 

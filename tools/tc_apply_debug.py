@@ -31,3 +31,13 @@ for (N, C, H, gs) in [(8, 64, 32, 64), (8, 128, 32, 32), (6, 64, 28, 64)]:
     dy = torch.randn_like(y)
     (dx,) = torch.autograd.grad(y, x, dy)
     print(f"   bwd: max|dx-dy| = {(dx-dy).abs().max().item():.3e}")
+
+# offset probe: non-zero running mean, data far from zero (the centring is applied after the product)
+for off in (2.0, 50.0):
+    torch.manual_seed(1)
+    N, C, H, gs = 8, 64, 32, 64
+    x = torch.randn(N, C, H, H, device=dev) + off
+    mu = torch.full((1, C, 1, 1), off, device=dev) + 0.1 * torch.randn(1, C, 1, 1, device=dev)
+    m = dwt_b200.WTransform2d(C, gs, running_m=mu.clone(), running_var=torch.eye(gs, device=dev).repeat(C // gs, 1, 1), eps=0.0).eval()
+    y = m(x)
+    print(f"offset probe off={off}: max|y-(x-mu)| = {(y - (x - mu)).abs().max().item():.3e}")
