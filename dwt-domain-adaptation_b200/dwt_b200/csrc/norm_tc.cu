@@ -6,11 +6,11 @@
 //
 // 2*gs flop per 4 bytes read puts these above the FP32-core ridge but far below the TF32
 // tensor ridge: on tcgen05 they are HBM-bound.  Structure of one CTA
-// (192 threads, persistent over a contiguous range of [64 channels x 32 pixels] tiles):
+// (320 threads, persistent over a contiguous range of [64 channels x 32 pixels] tiles):
 //
 //   warp 0      TMA producer: cp.async.bulk.tensor.3d (box 32 px x 64 ch x 1 image, SWIZZLE_128B)
 //               into an 8-stage shared-memory ring, mbarrier complete_tx.
-//   warps 2-5   transform: in place, tile <- RN_tf32(tile - shift[channel]) (zero outside the
+//   warps 2-9   transform: in place, tile <- RN_tf32(tile - shift[channel]) (zero outside the
 //               tensor), row sums in registers, fence.proxy.async, arrive on the stage's "ready" barrier.
 //               Round-to-NEAREST operands make the TF32 product errors zero-mean, so they average
 //               out over the M ~ 1e5..1e6 samples instead of biasing the covariance (truncation would).
@@ -35,10 +35,13 @@ namespace {
 
 using namespace tc;
 
-constexpr int kTcThreads = 192;
+constexpr int kTW = 8;                                  // transform warps (4 left the kernel transform-latency-bound: 0.74 of the HBM peak, 0.87 without the transform)
+constexpr int kTT = 32 * kTW;                           // transform threads
+constexpr int kPer = 512 / kTT;                         // 16-byte chunks of a tile per transform thread
+constexpr int kTcThreads = 64 + kTT;
 constexpr int kTilePx = 32, kTileCh = 64;
 constexpr int kTileBytes = kTileCh * kTilePx * 4;       // 8192
-constexpr int kStagesStats = 8, kStagesBwd = 4;
+constexpr int kStagesStats = 12, kStagesBwd = 6;      // 97 KB per CTA, two CTAs per SM: ~190 KB of loads in flight per SM
 constexpr int kTmemCols = 64;
 
 // ------------------------------------------------------------------------------------------
@@ -64,19 +67,24 @@ struct TileRange {
   }
 };
 
-// In-place transform of one landed tile by the 128 transform threads:
+// In-place transform of one landed tile by the kTT transform threads:
 //   v <- RN_tf32(v - shift[row]) inside the tensor, 0 outside; returns per-thread row sums of (v - shift).
-// Chunk q = tt + 128*i (16-byte units): row = q >> 3, physical chunk jp = q & 7, logical chunk = jp ^ (row & 7).
-__device__ __forceinline__ void transform_tile(float* tile, int tt, const float (&shift)[4], int px0, int HW, int ch0,
-                                               int C, float (&rowsum)[4]) {
+// Chunk q = tt + kTT*i (16-byte units): row = q >> 3, physical chunk jp = q & 7, logical chunk = jp ^ (row & 7).
+// Shared memory is addressed in its own state space (LDS/STS; a generic pointer costs an address-space check
+// and global-load latency class per access), all loads first.
+__device__ __forceinline__ void transform_tile(uint32_t tile, int tt, const float (&shift)[kPer], int px0, int HW, int ch0,
+                                               int C, float (&rowsum)[kPer]) {
+  float4 v[kPer];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int q = tt + 128 * i, row = q >> 3, jp = q & 7, j = jp ^ (row & 7);
-    float4* p = reinterpret_cast<float4*>(tile) + q;
-    float4 v = *p;
+  for (int i = 0; i < kPer; ++i)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                 : "r"(tile + 16u * (tt + kTT * i)));
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int q = tt + kTT * i, row = q >> 3, jp = q & 7, j = jp ^ (row & 7);
     const int px = px0 + 4 * j;
     const bool rowok = (ch0 + row) < C;
-    float e[4] = {v.x, v.y, v.z, v.w};
+    float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const bool ok = rowok && (px + k) < HW;
@@ -84,7 +92,8 @@ __device__ __forceinline__ void transform_tile(float* tile, int tt, const float 
       rowsum[i] += s;
       e[k] = round_tf32(s);
     }
-    *p = make_float4(e[0], e[1], e[2], e[3]);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile + 16u * (tt + kTT * i)), "f"(e[0]), "f"(e[1]),
+                 "f"(e[2]), "f"(e[3]) : "memory");
   }
 }
 
@@ -92,7 +101,7 @@ __device__ __forceinline__ void transform_tile(float* tile, int tt, const float 
 // the contraction kernel.  TWO = false: G = sum xs xs^T (stats).  TWO = true: R = sum dy xc^T.
 // ------------------------------------------------------------------------------------------
 template <bool TWO>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 2)
 tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
                    const float* __restrict__ x, const Geom gm, const float* __restrict__ save_mean,
                    float* __restrict__ shift_out, float* __restrict__ partial) {
@@ -108,7 +117,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const int ntiles = tr.end - tr.begin;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.ready[s], 4); mbar_init(&bars.empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.ready[s], kTW); mbar_init(&bars.empty[s], 1); }
     mbar_init(&bars.accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -135,8 +144,10 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   tc_fence_after();
   const uint32_t tmem_d = bars.tmem_slot;
 
-  float rowsum[4] = {0.f, 0.f, 0.f, 0.f};
-  const int tt = tid - 64;                       // transform thread index (warps 2..5)
+  float rowsum[kPer];
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) rowsum[i] = 0.f;
+  const int tt = tid - 64;                       // transform thread index (warps 2..9)
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -172,19 +183,17 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
   } else {
     // ===== transform warps =====
-    float shift[4];
+    float shift[kPer], zero[kPer], dummy[kPer];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) shift[i] = sShift[(tt + 128 * i) >> 3];
-    const float zero[4] = {0.f, 0.f, 0.f, 0.f};
-    float dummy[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < kPer; ++i) { shift[i] = sShift[(tt + kTT * i) >> 3]; zero[i] = 0.f; dummy[i] = 0.f; }
     for (int it = 0; it < ntiles; ++it) {
       const int s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(&bars.full[s], ph);
       const int t = tr.begin + it, n = t / tr.PB, pb = t - n * tr.PB;
-      float* tile = reinterpret_cast<float*>(smem + (size_t)s * NT * kTileBytes);
+      const uint32_t tile = smem_u32(smem + (size_t)s * NT * kTileBytes);
       if (TWO) {
         transform_tile(tile, tt, shift, pb * kTilePx, gm.HW, ch0, gm.C, dummy);                     // xc
-        transform_tile(tile + kTileBytes / 4, tt, zero, pb * kTilePx, gm.HW, ch0, gm.C, rowsum);    // dy, sums
+        transform_tile(tile + kTileBytes, tt, zero, pb * kTilePx, gm.HW, ch0, gm.C, rowsum);        // dy, sums
       } else {
         transform_tile(tile, tt, shift, pb * kTilePx, gm.HW, ch0, gm.C, rowsum);
       }
@@ -198,7 +207,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const int nacc = kTileCh * kTileCh + kTileCh;
   float* prow = partial + (((size_t)d * gridDim.y + sb) * gridDim.x + blockIdx.x) * nacc;
   if (warp >= 2) {
-    if (ntiles > 0) {
+    if (ntiles > 0 && warp < 6) {                  // four warps cover the four TMEM lane quadrants
       mbar_wait(&bars.accum, 0);
       tc_fence_after();
       const int quad = warp & 3;                   // TMEM lane quadrant this warp may access
@@ -214,17 +223,17 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
       }
       tc_fence_before();
-    } else {
-      for (int e = tt; e < kTileCh * kTileCh; e += 128) prow[e] = 0.f;
+    } else if (ntiles == 0) {
+      for (int e = tt; e < kTileCh * kTileCh; e += kTT) prow[e] = 0.f;
     }
     // row sums: the 8 lanes that share a row are consecutive
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kPer; ++i) {
       float s = rowsum[i];
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if ((tt & 7) == 0) prow[kTileCh * kTileCh + ((tt + 128 * i) >> 3)] = s;
+      if ((tt & 7) == 0) prow[kTileCh * kTileCh + ((tt + kTT * i) >> 3)] = s;
     }
   }
   __syncthreads();
@@ -263,6 +272,9 @@ int tc_init() {
   e = cudaFuncSetAttribute(tc_contract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(false));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(tc_contract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(true));
+  // two ~97 KB CTAs per SM need the full shared-memory carve-out
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_contract_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_contract_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) e = (cudaError_t)dense_init();
   if (e == cudaSuccess) return tc_apply_init();
   return (int)e;

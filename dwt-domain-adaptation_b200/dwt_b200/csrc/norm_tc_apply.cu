@@ -17,12 +17,12 @@
 //   centring is linear, M (x - shift) = M x - M shift, and is applied as one constant per row at the end.
 //
 // CTA = 2 + 4 + 4 warps (one input, two CTAs per SM) or 2 + 8 + 8 warps (two inputs, one CTA per SM), persistent over a contiguous range of 64-pixel tiles of one (domain, super-block):
-//   warp 0     TMA producer into a RAW ring (2 boxes of 32 px x 64 ch per input tensor and slot,
+//   warp 0     TMA producer into a RAW ring (4 boxes of 32 px x 64 ch per slot,
 //              SWIZZLE_128B_ATOM_32B: the only layout the tensor core takes for an MN-major tf32 operand)
-//   warp 1     MMA issuer (tcgen05.mma kind::tf32, M=128 N=64 K=8; A resident in TMEM, B MN-major), TMEM owner
+//   warp 1     MMA issuer (tcgen05.mma kind::tf32, M=128 N=128 K=8; A resident in TMEM, B MN-major), TMEM owner
 //   TW warps   transform: raw slot -> lo slot
-//   EW warps   epilogue: tcgen05.ld of this warp's lane quadrant x (64 or 32) columns, hi/lo row halves folded
-//              by a half-warp exchange in which each half keeps half of the columns, 256-bit stores.
+//   EW warps   epilogue: tcgen05.ld of this warp's lane quadrant x 64 columns, hi/lo row halves folded by a
+//              half-warp exchange in which each half keeps 32 columns (one full 128-byte line per lane), 256-bit stores.
 //              (One merged worker group doing transform(it) then epilogue(it-1) serialised transform -> MMA ->
 //              epilogue into one chain: 1.5 us per two-input tile against 0.6 us of tensor time.)
 // The raw ring is deeper than the lo ring: a raw slot is busy from the TMA issue to the end of its MMAs (one HBM
@@ -49,21 +49,22 @@ constexpr int kBoxBytes = kCh * kBoxPx * 4;          // 8192
 constexpr int kMatCols = 64;                         // TMEM columns per resident matrix
 constexpr int kMaxRaw = 6, kLo = 2;
 
-// One STEP = one input tensor's [64 ch x TPX px] tile: a raw ring slot filled by TMA, a lo ring slot filled by the
-// transform warps, 16 MMAs (2 terms x 8 k-steps of N = TPX) accumulating into the tile's TMEM accumulator.
-// The issue cost of a tcgen05.mma is ~90 cycles whatever its N (measured: one warp issuing 32 N=64 MMAs per
-// two-input tile was 90 % busy with the tensor pipe 35 % active), so the two-input kernel uses N = 128:
-//   one input : TPX  64, 4 raw + 2 lo slots of 16 KB =  97 KB, 2 + 4 + 4 warps, two CTAs per SM, 256 TMEM columns
-//   two inputs: TPX 128, 5 raw + 2 lo slots of 32 KB = 225 KB, 2 + 8 + 8 warps, one CTA per SM,  512 TMEM columns
+// One STEP = one input tensor's [64 ch x 128 px] tile: a raw ring slot filled by TMA, a lo ring slot filled by the
+// transform warps, 16 MMAs (2 terms x 8 k-steps of N = 128) accumulating into the tile's TMEM accumulator.
+// N = 128 because a tcgen05.mma costs its issuing thread ~90 cycles whatever its N: with N = 64 the one warp
+// issuing 32 MMAs per two-input tile was 90 % busy while the tensor pipe was 35 % active and the kernel ran at 0.70 of
+// the HBM peak; N = 128 halves the instruction count per pixel (0.84).  The one-input kernel is bound by its memory
+// access pattern either way (same time at N = 64 with two CTAs per SM) and shares the configuration:
+//   5 raw + 2 lo slots of 32 KB = 225 KB, 2 + 8 + 8 warps, one CTA per SM, 512 TMEM columns
 template <int NIN> struct ApCfg {
-  static constexpr int TPX = NIN == 1 ? 64 : 128;
+  static constexpr int TPX = 128;
   static constexpr int NBOX = TPX / kBoxPx;
-  static constexpr int TW = NIN == 1 ? 4 : 8;          // transform warps
-  static constexpr int EW = NIN == 1 ? 4 : 8;          // epilogue warps (per SM: 8 + 8 either way)
+  static constexpr int TW = 8;                         // transform warps
+  static constexpr int EW = 8;                         // epilogue warps
   static constexpr int THREADS = 64 + 32 * (TW + EW);
-  static constexpr int RAW = NIN == 1 ? 4 : 5;
+  static constexpr int RAW = 5;
   static constexpr int SLOT = NBOX * kBoxBytes;
-  static constexpr int TMEM = NIN == 1 ? 256 : 512;    // 2 accumulators of TPX columns + NIN matrices of 64
+  static constexpr int TMEM = 512;                     // 2 accumulators of TPX columns + NIN matrices of 64
   static constexpr size_t SMEM = (size_t)(RAW + kLo) * SLOT + 1024;
 };
 
@@ -118,7 +119,7 @@ __device__ __forceinline__ void lo_box(uint32_t raw, uint32_t lo, int tt) {
 // for l >= 16, so the two halves that must be added end up 16 lanes apart IN THE SAME WARP and the
 // epilogue folds them with one shuffle per value -- no shared-memory staging at all.
 template <int NIN>
-__global__ void __launch_bounds__(ApCfg<NIN>::THREADS, NIN == 1 ? 2 : 1)
+__global__ void __launch_bounds__(ApCfg<NIN>::THREADS, 1)
 tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Geom gm,
                 const ApplyArgs args) {
   using Cfg = ApCfg<NIN>;
@@ -327,7 +328,7 @@ int tc_apply_init() {
   g_encode_ap = reinterpret_cast<EncodeTiledFn>(fn);
   e = cudaFuncSetAttribute(tc_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ap_smem<1>());
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_apply_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ap_smem<2>());
-  // two 97 KB CTAs (or one 225 KB CTA) per SM need the full shared-memory carve-out
+  // a 225 KB CTA needs the full shared-memory carve-out
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_apply_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_apply_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   return (int)e;
