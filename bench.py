@@ -79,6 +79,8 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def __enter__(self):
+        if os.environ.get("DWT_NO_CLOCK_SAMPLER"):          # diagnosis only: is the sampler perturbing the run?
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -458,7 +460,9 @@ def run_microbench(args, device, rank):
     N, C, H, gs = args.micro_n, 256, 56, args.micro_gs
     torch.manual_seed(0)
     mix = torch.randn(C, C, device=device) / C ** 0.5 + torch.eye(C, device=device)
-    x = (torch.einsum("dc,nchw->ndhw", mix, torch.randn(N, C, H, H, device=device)) + 2.0).requires_grad_(True)
+    # .contiguous(): einsum returns a permuted view, and a strided input would add a layout copy (and its backward) of
+    # the 822 MB tensor to every step -- 0.5 ms that is not the layer's
+    x = (torch.einsum("dc,nchw->ndhw", mix, torch.randn(N, C, H, H, device=device)) + 2.0).contiguous().requires_grad_(True)
     dy = torch.randn(N, C, H, H, device=device)
     m = dwt_b200.WTransform2d(C, gs).to(device).train()
 
