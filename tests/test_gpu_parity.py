@@ -678,3 +678,35 @@ def test_collect_stats_replicated_matches_reference_form(dev):
         elif k.endswith("num_batches_tracked"):
             assert int(v) == int(b_stock[k]) == int(b_triple[k]), k
     assert not single.training                               # collect_stats restores the caller's mode
+
+
+def test_tensor_core_path_is_graph_capturable(dev):
+    """The TMA/tcgen05 path (descriptor encode + 6 launches per fwd+bwd) must be capturable into a CUDA graph --
+    nothing on it may synchronise, allocate through the driver or touch the context during capture -- and a
+    replay must reproduce the eager result bit for bit (fixed-order reductions everywhere)."""
+    import dwt_b200
+    torch.manual_seed(3)
+    nimg, c, hw, gs = 8, 128, 24, 64                       # N*HW = 4608 >= 4096 -> tensor-core kernels
+    x = (torch.randn(nimg, c, hw, hw, device=dev) + 2.0).requires_grad_(True)
+    dy = torch.randn(nimg, c, hw, hw, device=dev)
+    m = dwt_b200.WTransform2d(c, gs).to(dev).train()
+
+    def step():
+        y = m(x)
+        return y, torch.autograd.grad(y, x, dy)[0]
+
+    for _ in range(2):
+        y_e, dx_e = step()                                 # eager, default stream
+    torch.cuda.synchronize(dev)
+    side = torch.cuda.Stream(dev)                          # the usual pre-capture warm-up on a side stream
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        y_g, dx_g = step()
+    g.replay()
+    torch.cuda.synchronize(dev)
+    assert torch.equal(y_g, y_e) and torch.equal(dx_g, dx_e)
