@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdwt_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_DOMAINS = 4
 MAX_GROUP_SIZE = 64
 MODE_TRAIN, MODE_EVAL = 0, 1
@@ -49,6 +49,10 @@ _SIGNATURES = {
                                        _c_float_p, _c_float_p, ctypes.c_void_p]),
     "dwt_head_loss_fwd_bwd": (ctypes.c_int, [_c_float_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_float,
                                              _c_float_p, _c_float_p, ctypes.c_void_p]),
+    "dwt_augment_pair": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_float_p,
+                                        ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _c_float_p,
+                                        _c_float_p, ctypes.c_int, ctypes.c_void_p]),
     "dwt_launch_count": (ctypes.c_int64, []),
     "dwt_profile_begin": (None, []),
     "dwt_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

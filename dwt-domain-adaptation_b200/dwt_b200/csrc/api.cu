@@ -535,6 +535,28 @@ int dwt_head_loss_fwd_bwd(const float* logits, const int64_t* labels, int64_t B,
   return check_launch("head loss kernel");
 }
 
+int dwt_augment_pair(const uint8_t* images, int64_t B, int src_h, int src_w, int crop, const int32_t* crop_plain,
+                     const int32_t* crop_aug, const uint8_t* flip, const float* affine, const float* mean,
+                     const float* stdv, float* out_plain, float* out_aug, int layout, dwt_stream_t stream) {
+  if (!images || !mean || !stdv) return fail(DWT_E_INVALID, "null pointer argument");
+  if (!out_plain && !out_aug) return fail(DWT_E_INVALID, "at least one of out_plain / out_aug is needed");
+  if (out_plain && !crop_plain) return fail(DWT_E_INVALID, "out_plain needs crop_plain");
+  if (out_aug && (!crop_aug || !flip || !affine)) return fail(DWT_E_INVALID, "out_aug needs crop_aug, flip and affine");
+  if (B <= 0 || B > 65535 || src_h <= 0 || src_w <= 0 || src_h > 16384 || src_w > 16384)
+    return fail(DWT_E_INVALID, "bad image batch [%lld,%d,%d,3]", (long long)B, src_h, src_w);
+  if (crop <= 0 || crop > src_h || crop > src_w) return fail(DWT_E_INVALID, "crop %d does not fit %dx%d", crop, src_h, src_w);
+  if (layout != 0 && layout != DWT_LAYOUT_NHWC) return fail(DWT_E_INVALID, "layout must be 0 (NCHW) or DWT_LAYOUT_NHWC");
+  for (int c = 0; c < 3; ++c)
+    if (!(stdv[c] != 0.f)) return fail(DWT_E_INVALID, "std[%d] must be non-zero", c);
+  {
+    const double px = (double)B * crop * crop;
+    Launch l("augment_pair", nullptr, px * 3 * ((out_plain ? 5.0 : 0.0) + (out_aug ? 5.0 : 0.0)), (cudaStream_t)stream);
+    dwt::augment_pair_launch(images, (int)B, src_h, src_w, crop, crop_plain, crop_aug, flip, affine, mean, stdv, out_plain,
+                             out_aug, layout != 0, (cudaStream_t)stream);
+  }
+  return check_launch("augmentation kernel");
+}
+
 int64_t dwt_launch_count(void) { return g_launches.load(); }
 
 void dwt_profile_begin(void) {

@@ -1,5 +1,7 @@
 // Host-side launch entry points of the kernel families (internal to libdwt_b200.so).
 #pragma once
+#include <stdint.h>
+
 #include "dwt_common.cuh"
 
 namespace dwt {
@@ -77,6 +79,10 @@ void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, 
                   const float* mean, const float* w, const float* gamma, const float* beta, cudaStream_t st);
 
 // MEC loss (mec.cu)
+// paired target augmentation (augment.cu); mean / stdv are HOST arrays of 3
+void augment_pair_launch(const uint8_t* images, int B, int SH, int SW, int CR, const int* crop_plain, const int* crop_aug,
+                         const uint8_t* flip, const float* affine, const float* mean, const float* stdv,
+                         float* out_plain, float* out_aug, int nhwc, cudaStream_t st);
 void head_loss_launch(const float* logits, const long long* labels, int B, int K, float lambda, float* losses,
                       float* grad, cudaStream_t st);
 void mec_launch(const float* x, const float* y, int N, int K, float* loss, float* gx, float* gy, cudaStream_t st);

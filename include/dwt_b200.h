@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DWT_B200_ABI_VERSION 2
+#define DWT_B200_ABI_VERSION 3
 #define DWT_MAX_DOMAINS 4
 #define DWT_MAX_GROUP_SIZE 64
 
@@ -147,6 +147,23 @@ DWT_API int dwt_mec_fwd_bwd(const float *x, const float *y, int64_t N, int64_t K
  */
 DWT_API int dwt_head_loss_fwd_bwd(const float *logits, const int64_t *labels, int64_t B, int64_t K, float lambda,
                           float *losses, float *grad, dwt_stream_t stream);
+
+/*
+ * Paired target augmentation: both views the reference's loader derives from one image
+ * (utils/folder.py:127-147 applying the two pipelines of resnet50_dwt_mec_officehome.py:526-542), in one launch.
+ *   images      [B, src_h, src_w, 3] uint8, already resized (device)
+ *   crop_plain  [B, 2] int32 (top, left) of the plain view's RandomCrop;  crop_aug  [B, 2] of the augmented view's
+ *   flip        [B] uint8, RandomHorizontalFlip outcome;  affine [B, 6] float32, the 2x3 matrix that
+ *               _random_affine_augmentation (:481-487) hands to cv2.warpAffine     (all device pointers)
+ *   mean, stdv  HOST arrays of 3 (Normalize, :530)
+ *   out_plain / out_aug  [B, 3, crop, crop] float32 (NCHW, layout 0) or [B, crop, crop, 3] (DWT_LAYOUT_NHWC); either
+ *               may be NULL (the source domain has no augmented view).
+ * The affine warp reproduces cv2.warpAffine (INTER_LINEAR, constant border 0) bit for bit; the reference's
+ * GaussianBlur has kernel size 1 (sigma 0.1, :489-491) and is the identity.  Crop corners are clamped into the image.
+ */
+DWT_API int dwt_augment_pair(const uint8_t *images, int64_t B, int src_h, int src_w, int crop, const int32_t *crop_plain,
+                     const int32_t *crop_aug, const uint8_t *flip, const float *affine, const float *mean,
+                     const float *stdv, float *out_plain, float *out_aug, int layout, dwt_stream_t stream);
 
 /*
  * Measurement hooks (used by bench.py; not part of the reference's surface).

@@ -710,3 +710,63 @@ def test_tensor_core_path_is_graph_capturable(dev):
     g.replay()
     torch.cuda.synchronize(dev)
     assert torch.equal(y_g, y_e) and torch.equal(dx_g, dx_e)
+
+
+# --------------------------------------------------------------------------- paired augmentation (§8f-4)
+def _aug_inputs(g, dev):
+    return dict(crop_plain=torch.tensor(g("crop_plain"), device=dev), crop_aug=torch.tensor(g("crop_aug"), device=dev),
+                flip=torch.tensor(g("flip"), device=dev), affine=torch.tensor(g("affine"), device=dev))
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("case", ["ref", "strong", "tiny"])
+def test_augmentation_is_bit_exact_vs_reference_golden(case, channels_last, dev):
+    """One launch must give, bit for bit, what the reference's CPU workers give (torchvision crop/flip/to_tensor/
+    normalize around the reference's cv2.warpAffine call) -- integer/fixed-point sampling, so the bar is equality."""
+    from dwt_b200 import PairedAugment
+    z = np.load(os.path.join(HERE, "augment.npz"))
+    g = lambda k: z[f"{case}/{k}"]                                  # noqa: E731
+    plain, aug = PairedAugment(crop=int(g("crop")))(torch.tensor(g("images"), device=dev), channels_last=channels_last,
+                                                     **_aug_inputs(g, dev))
+    assert plain.is_contiguous(memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    assert np.array_equal(plain.cpu().numpy(), g("plain")) and np.array_equal(aug.cpu().numpy(), g("aug"))
+
+
+def test_augmentation_full_size_into_model_input(dev):
+    """Office-Home geometry (256 -> 224), the views written straight into the target | target-aug thirds of the
+    model's [3B, 3, 224, 224] input; checked against the numpy oracle (itself pinned bit-exact to the reference)."""
+    from dwt_b200 import PairedAugment, draw_params
+    from oracle import augment_oracle as A
+    rng = np.random.default_rng(8)
+    B = 6
+    images = rng.integers(0, 256, (B, 256, 256, 3), dtype=np.uint8)
+    images[0, :8] = 255; images[1, :, -8:] = 0                        # saturated borders
+    p = draw_params(B, 256, 224, rng, affine_sigma=0.1)
+    p["affine"][0] = torch.tensor([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])  # identity warp = plain crop of the aug corner
+    p["affine"][1] = torch.tensor([[0.5, 0.4, 0.0], [-0.4, 0.6, 0.0]])  # far outside the reference's range
+    batch = torch.zeros(3 * B, 3, 224, 224, device=dev)
+    pa = PairedAugment(crop=224)
+    gp = {k: v.to(dev) for k, v in p.items()}
+    pa(torch.tensor(images, device=dev), out_plain=batch[B:2 * B], out_aug=batch[2 * B:], **gp)
+    src = rng.integers(0, 256, (B, 256, 256, 3), dtype=np.uint8)
+    pa(torch.tensor(src, device=dev), crop_plain=gp["crop_plain"], out_plain=batch[:B], want_aug=False)   # source domain
+    o_plain, o_aug = A.paired(images, p["crop_plain"].numpy(), p["crop_aug"].numpy(), p["flip"].numpy(),
+                              p["affine"].numpy(), 224)
+    o_src, _ = A.paired(src, p["crop_plain"].numpy(), p["crop_aug"].numpy(), np.zeros(B, np.uint8), p["affine"].numpy(), 224)
+    out = batch.cpu().numpy()
+    assert np.array_equal(out[B:2 * B], o_plain) and np.array_equal(out[2 * B:], o_aug) and np.array_equal(out[:B], o_src)
+
+
+def test_augmentation_errors(dev):
+    from dwt_b200 import PairedAugment, _native
+    pa = PairedAugment(crop=8)
+    img = torch.zeros(2, 6, 6, 3, dtype=torch.uint8, device=dev)
+    cp = torch.zeros(2, 2, dtype=torch.int32, device=dev)
+    with pytest.raises(_native.NativeError):
+        pa(img, crop_plain=cp, want_aug=False)                        # crop larger than the image
+    with pytest.raises(ValueError):
+        pa(img.float(), crop_plain=cp, want_aug=False)                # not uint8
+    with pytest.raises(ValueError):
+        PairedAugment(crop=4)(img, crop_plain=cp)                     # augmented view without its parameters
+    with pytest.raises(_native.NativeError):
+        PairedAugment(crop=4)(img.cpu(), crop_plain=cp, want_aug=False)

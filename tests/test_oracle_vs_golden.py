@@ -91,3 +91,32 @@ def test_closed_form_backward_matches_autograd_fp64():
         (dx_ref,) = torch.autograd.grad(m(xt), xt, torch.tensor(dy))
         _, mean, w, *_ = O.whiten_forward(x, gs)
         assert rel_err(O.whiten_backward(x, dy, mean, w), dx_ref.numpy()) < 1e-11
+
+
+# --------------------------------------------------------------------------- paired augmentation (§8f-4)
+@pytest.mark.parametrize("case", ["ref", "strong", "tiny"])
+def test_augmentation_oracle_is_bit_exact_vs_reference(case):
+    """tests/golden/augment.npz = the reference's own _random_affine_augmentation / _gaussian_blur inside the
+    torchvision pipeline; the numpy restatement (fixed-point cv2.warpAffine and all) must agree bit for bit."""
+    from oracle import augment_oracle as A
+    z = np.load(os.path.join(HERE, "augment.npz"))
+    g = lambda k: z[f"{case}/{k}"]                                  # noqa: E731
+    plain, aug = A.paired(g("images"), g("crop_plain"), g("crop_aug"), g("flip"), g("affine"), int(g("crop")))
+    assert plain.dtype == np.float32 and aug.dtype == np.float32
+    assert np.array_equal(plain, g("plain")) and np.array_equal(aug, g("aug"))
+
+
+def test_augmentation_draws_have_the_reference_distributions():
+    """Host logic of the product's draw_params: shapes, dtypes, ranges, moments (resnet50_dwt_mec_officehome.py:481-483,
+    535-537: crop corners uniform, flip p = 0.5, affine = I + N(0, 0.1) with a zero translation column)."""
+    import torch
+    from dwt_b200.augment import draw_params
+    p = draw_params(4096, 256, 224, np.random.default_rng(0))
+    assert p["crop_plain"].dtype == torch.int32 and tuple(p["crop_aug"].shape) == (4096, 2)
+    assert int(p["crop_plain"].min()) == 0 and int(p["crop_plain"].max()) == 32
+    assert not torch.equal(p["crop_plain"], p["crop_aug"])           # the two views crop independently
+    assert p["flip"].dtype == torch.uint8 and 0.45 < float(p["flip"].float().mean()) < 0.55
+    a = p["affine"].numpy()
+    assert a.dtype == np.float32 and a.shape == (4096, 2, 3) and np.all(a[:, :, 2] == 0)
+    dev = a[:, :, :2] - np.eye(2, dtype=np.float32)
+    assert abs(dev.mean()) < 5e-3 and 0.095 < dev.std() < 0.105
