@@ -142,14 +142,14 @@ def ptr_array(tensors):
     return ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))
 
 
-def require_cuda(*tensors) -> torch.device:
+def require_cuda(*tensors, any_dtype=False) -> torch.device:
     dev = None
     for t in tensors:
         if t is None:
             continue
         if not t.is_cuda:
             raise NativeError("dwt_b200 runs on CUDA tensors only (no CPU fallback); got a tensor on " + str(t.device))
-        if t.dtype != torch.float32:
+        if t.dtype != torch.float32 and not any_dtype:
             raise NativeError("dwt_b200 computes in float32; got " + str(t.dtype))
         if dev is None:
             dev = t.device

@@ -53,7 +53,7 @@ class PairedAugment:
         -> (plain, aug)  (aug is None when want_aug=False: the source domain has no augmented view)."""
         if images.dim() != 4 or images.shape[3] != 3 or images.dtype != torch.uint8:
             raise ValueError(f"expected a [B, H, W, 3] uint8 batch, got {tuple(images.shape)} {images.dtype}")
-        dev = nv.require_cuda(images)
+        dev = nv.require_cuda(images, any_dtype=True)
         images = images.contiguous()
         b, sh, sw = images.shape[0], images.shape[1], images.shape[2]
         fmt = torch.channels_last if channels_last else torch.contiguous_format
@@ -71,7 +71,8 @@ class PairedAugment:
                 raise ValueError(f"{name} is required")
             if tuple(t.shape) != shape or t.dtype != dtype:
                 raise ValueError(f"{name} must be {dtype} of shape {shape}, got {t.dtype} {tuple(t.shape)}")
-            nv.require_cuda(t)
+            if nv.require_cuda(t, any_dtype=True) != dev:
+                raise nv.NativeError(f"{name} is on {t.device}, the images on {dev}")
             return t.contiguous()
 
         crop_plain = param(crop_plain, (b, 2), torch.int32, "crop_plain")

@@ -696,7 +696,11 @@ def test_tensor_core_path_is_graph_capturable(dev):
         return y, torch.autograd.grad(y, x, dy)[0]
 
     for _ in range(2):
-        y_e, dx_e = step()                                 # eager, default stream
+        y, dx = step()                                     # eager, default stream
+    # keep values, not the autograd graph: a live graph pins x's AccumulateGrad node to the default stream, and the
+    # engine's end-of-backward sync with that stream is illegal inside a capture (a PyTorch rule, not the library's)
+    y_e, dx_e = y.detach().clone(), dx.detach().clone()
+    del y, dx
     torch.cuda.synchronize(dev)
     side = torch.cuda.Stream(dev)                          # the usual pre-capture warm-up on a side stream
     side.wait_stream(torch.cuda.current_stream(dev))
