@@ -49,50 +49,68 @@ __device__ __forceinline__ void store_pixel(float* out, const AugArgs& a, int b,
 }
 
 __global__ void __launch_bounds__(256) augment_pair_kernel(const AugArgs a) {
+  // Per-CTA tables instead of per-pixel IEEE divisions (an exact division is ~10 instructions and the augmented
+  // view needs 15 per pixel): a uint8 has 256 values, so ToTensor (and, for the plain view, Normalize as well) is
+  // a lookup of the very same correctly rounded results.  The inverse matrix is one thread's work per CTA.
+  __shared__ float sLut[3][256];
+  __shared__ double sM[6];
   const int pix = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y, branch = blockIdx.z;
+  if ((branch == 0 ? a.out_plain : a.out_aug) == nullptr) return;               // uniform per CTA
+  if (branch == 0) {
+    for (int c = 0; c < 3; ++c)
+      sLut[c][threadIdx.x] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)threadIdx.x, 255.f), a.mean[c]), a.stdv[c]);
+  } else {
+    sLut[0][threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.f);
+    if (threadIdx.x == 0) {
+      // cv2::invertAffineTransform in double, no contraction
+      const float* Mf = a.affine + 6 * b;
+      const double M0 = Mf[0], M1 = Mf[1], M2 = Mf[2], M3 = Mf[3], M4 = Mf[4], M5 = Mf[5];
+      double D = __dsub_rn(__dmul_rn(M0, M4), __dmul_rn(M1, M3));
+      D = D != 0.0 ? __ddiv_rn(1.0, D) : 0.0;
+      const double m0 = __dmul_rn(M4, D), m4 = __dmul_rn(M0, D), m1 = __dmul_rn(M1, -D), m3 = __dmul_rn(M3, -D);
+      sM[0] = m0; sM[1] = m1; sM[3] = m3; sM[4] = m4;
+      sM[2] = __dsub_rn(__dmul_rn(-m0, M2), __dmul_rn(m1, M5));
+      sM[5] = __dsub_rn(__dmul_rn(-m3, M2), __dmul_rn(m4, M5));
+    }
+  }
+  __syncthreads();
   if (pix >= a.CR * a.CR) return;
   const int y = pix / a.CR, x = pix - y * a.CR;
   const uint8_t* img = a.images + (size_t)b * a.SH * a.SW * 3;
   float v[3];
   if (branch == 0) {
-    if (a.out_plain == nullptr) return;
     const int top = clampi(a.crop_plain[2 * b], 0, a.SH - a.CR), left = clampi(a.crop_plain[2 * b + 1], 0, a.SW - a.CR);
     const uint8_t* s = img + ((size_t)(top + y) * a.SW + left + x) * 3;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)s[c], 255.f), a.mean[c]), a.stdv[c]);
+    for (int c = 0; c < 3; ++c) v[c] = sLut[c][s[c]];
     store_pixel(a.out_plain, a, b, y, x, v);
     return;
   }
-  if (a.out_aug == nullptr) return;
   const int top = clampi(a.crop_aug[2 * b], 0, a.SH - a.CR), left = clampi(a.crop_aug[2 * b + 1], 0, a.SW - a.CR);
   const bool flip = a.flip[b] != 0;
-  // cv2::invertAffineTransform in double, no contraction
-  const float* Mf = a.affine + 6 * b;
-  const double M0 = Mf[0], M1 = Mf[1], M2 = Mf[2], M3 = Mf[3], M4 = Mf[4], M5 = Mf[5];
-  double D = __dsub_rn(__dmul_rn(M0, M4), __dmul_rn(M1, M3));
-  D = D != 0.0 ? __ddiv_rn(1.0, D) : 0.0;
-  const double m0 = __dmul_rn(M4, D), m4 = __dmul_rn(M0, D), m1 = __dmul_rn(M1, -D), m3 = __dmul_rn(M3, -D);
-  const double m2 = __dsub_rn(__dmul_rn(-m0, M2), __dmul_rn(m1, M5));
-  const double m5 = __dsub_rn(__dmul_rn(-m3, M2), __dmul_rn(m4, M5));
-  // fixed-point source position (AB_BITS = 10, INTER_BITS = 5)
-  const long long X = ((long long)__double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m1, (double)y), m2), 1024.0)) + 16 +
-                       (long long)__double2int_rn(__dmul_rn(__dmul_rn(m0, (double)x), 1024.0))) >> 5;
-  const long long Y = ((long long)__double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m4, (double)y), m5), 1024.0)) + 16 +
-                       (long long)__double2int_rn(__dmul_rn(__dmul_rn(m3, (double)x), 1024.0))) >> 5;
-  const long long sx = X >> 5, sy = Y >> 5;
+  const double m0 = sM[0], m1 = sM[1], m2 = sM[2], m3 = sM[3], m4 = sM[4], m5 = sM[5];
+  // fixed-point source position (AB_BITS = 10, INTER_BITS = 5); OpenCV keeps these in 32-bit ints as well
+  const int X = (__double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m1, (double)y), m2), 1024.0)) + 16 +
+                 __double2int_rn(__dmul_rn(__dmul_rn(m0, (double)x), 1024.0))) >> 5;
+  const int Y = (__double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m4, (double)y), m5), 1024.0)) + 16 +
+                 __double2int_rn(__dmul_rn(__dmul_rn(m3, (double)x), 1024.0))) >> 5;
+  const int sx = X >> 5, sy = Y >> 5;
   const float fx = (float)(X & 31) * 0.03125f, fy = (float)(Y & 31) * 0.03125f;     // exact
   const float w00 = __fmul_rn(1.f - fy, 1.f - fx), w01 = __fmul_rn(1.f - fy, fx);
   const float w10 = __fmul_rn(fy, 1.f - fx), w11 = __fmul_rn(fy, fx);
+  // the four taps of the cropped (and flipped) image; 32-bit byte offsets inside this image (< 2^31 by the size check)
+  const bool okx0 = (unsigned)sx < (unsigned)a.CR, okx1 = (unsigned)(sx + 1) < (unsigned)a.CR;
+  const bool oky0 = (unsigned)sy < (unsigned)a.CR, oky1 = (unsigned)(sy + 1) < (unsigned)a.CR;
+  const int col0 = left + (flip ? a.CR - 1 - sx : sx), dcol = flip ? -3 : 3, drow = a.SW * 3;
+  const int o00 = ((top + sy) * a.SW + col0) * 3;
+  const float* lut = sLut[0];
   float t[4][3];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const long long yy = sy + (k >> 1), xx = sx + (k & 1);
-    const bool ok = yy >= 0 && yy < a.CR && xx >= 0 && xx < a.CR;
-    // tap (yy, xx) of the cropped, flipped, /255 image
-    const int sxx = flip ? (a.CR - 1 - (int)xx) : (int)xx;
-    const uint8_t* s = img + ((size_t)(top + (ok ? (int)yy : 0)) * a.SW + left + (ok ? sxx : 0)) * 3;
+    const bool ok = ((k & 1) ? okx1 : okx0) && ((k >> 1) ? oky1 : oky0);
+    const int o = o00 + ((k & 1) ? dcol : 0) + ((k >> 1) ? drow : 0);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) t[k][c] = ok ? __fdiv_rn((float)s[c], 255.f) : 0.f;
+    for (int c = 0; c < 3; ++c) t[k][c] = ok ? lut[img[o + c]] : 0.f;
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
