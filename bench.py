@@ -547,6 +547,13 @@ def run_microbench(args, device, rank):
     fams = {k: dict(v, gbs=v["bytes"] / (v["ms"] * 1e-3) / 1e9, us_per_launch=1e3 * v["ms"] / v["launches"])
             for k, v in prof.items() if v["ms"] > 0}
     gbs = total_bytes * args.steps / (ms * 1e-3) / 1e9
+    ratio, ratio_src = None, None
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))["tensor_core_path"]
+        if gs >= 8:
+            ratio, ratio_src = tab["traffic_over_algorithmic"]["fwd+bwd (all launches)"], tab["source"]
+    except Exception:
+        pass
     print(json.dumps({
         "metric": "WTransform2d fwd+bwd microbench", "value": args.steps / (ms * 1e-3), "unit": "iterations/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -556,7 +563,8 @@ def run_microbench(args, device, rank):
                    "l2": f"tensor of {elems * 4 / 1e6:.0f} MB > 126 MB L2",
                    "launch": "cuda-graph replay" if graph is not None else "eager"},
         "roofline": {"bound": "hbm", "kernel": "fwd+bwd (4 launches)", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                     "frac": gbs / peak, "traffic": None, "peak_source": peak_src},
+                     "frac": gbs / peak, "traffic": ratio * total_bytes if ratio else None, "traffic_source": ratio_src,
+                     "algorithmic_bytes_per_step": total_bytes, "peak_source": peak_src},
         "kernels": fams, "clocks": clocks.summary(),
     }))
 
