@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) augment_pair_kernel(const AugArgs a) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const bool ok = ((k & 1) ? okx1 : okx0) && ((k >> 1) ? oky1 : oky0);
-    const int o = o00 + ((k & 1) ? dcol : 0) + ((k >> 1) ? drow : 0);
+    // an out-of-image tap reads the crop origin instead (always a valid address) and is then discarded
+    const int o = ok ? o00 + ((k & 1) ? dcol : 0) + ((k >> 1) ? drow : 0) : (top * a.SW + left) * 3;
 #pragma unroll
     for (int c = 0; c < 3; ++c) t[k][c] = ok ? lut[img[o + c]] : 0.f;
   }
