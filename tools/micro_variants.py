@@ -1,4 +1,6 @@
-"""Timing experiments on the tc apply kernels: DWT_TC_DBG bit 1 = no stores, 2 = no transform, 4 = no MMA."""
+"""Per-kernel times of the config-2 whitening layer (CUDA-event brackets of the library), repeated per argument.
+The DWT_TC_DBG switches this script drove during the round-1 experiments (profiles/tc_apply_experiments_r01.md)
+were removed from the kernels again; the arguments now only label repeated runs."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "dwt-domain-adaptation_b200"))
 import torch
