@@ -105,3 +105,22 @@ def test_module_surface_matches_reference():
     bn.load_state_dict(old)
     crit = consensus_loss.MinEntropyConsensusLoss(num_classes=65, device="cpu")
     assert crit.num_classes == 65 and crit.device == "cpu"
+
+
+def test_tensor_core_objects_contain_blackwell_instructions(built_lib):
+    """The large-group kernels must really be TMA + tcgen05 code: their sm_100a objects carry the SASS mnemonics of
+    tensor-memory MMAs (UTCHMMA), bulk tensor loads (UTMALDG), tensor-memory loads/stores (LDTM/STTM) and
+    transaction mbarriers (SYNCS) -- B200_PROFILING.md's proof list; an mma.sync/FFMA fallback would show none."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib_dir = os.path.dirname(built_lib.LIB_PATH)
+    want = {"norm_tc.o": ["UTCHMMA", "UTMALDG", "LDTM", "SYNCS.PHASECHK.TRANS64.TRYWAIT"],
+            "norm_tc_apply.o": ["UTCHMMA", "UTMALDG", "LDTM", "STTM", "STG.E.ENL2.256"]}
+    for obj, mnemonics in want.items():
+        sass = subprocess.run([cuobjdump, "-sass", os.path.join(lib_dir, obj)], capture_output=True, text=True).stdout
+        assert "sm_100a" in sass or "SM100" in sass.upper(), obj
+        for m in mnemonics:
+            assert m in sass, f"{obj}: no {m} in SASS"
