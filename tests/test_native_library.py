@@ -124,3 +124,37 @@ def test_tensor_core_objects_contain_blackwell_instructions(built_lib):
         assert "sm_100a" in sass or "SM100" in sass.upper(), obj
         for m in mnemonics:
             assert m in sass, f"{obj}: no {m} in SASS"
+
+
+def test_extensions_refuse_cpu_tensors_too(built_lib):
+    """The extension entry points (fused site, head loss, augmentation) have no CPU path either."""
+    import dwt_b200
+    mods = [dwt_b200.WTransform2d(8, 4).train() for _ in range(3)]
+    g, b = torch.ones(8, 1, 1), torch.zeros(8, 1, 1)
+    with pytest.raises(built_lib.NativeError):
+        dwt_b200.DomainTripleNorm("whiten", 8, 4)(torch.randn(6, 8, 4, 4), mods, g, b)
+    with pytest.raises(built_lib.NativeError):
+        dwt_b200.DomainTripleNorm("whiten", 8, 4)(torch.randn(2, 8, 4, 4), mods, g, b, replicated=True)
+    with pytest.raises(built_lib.NativeError):
+        dwt_b200.HeadLoss(5, 0.1)(torch.randn(6, 5), torch.zeros(2, dtype=torch.int64))
+    with pytest.raises(built_lib.NativeError):
+        dwt_b200.PairedAugment(crop=4)(torch.zeros(2, 6, 6, 3, dtype=torch.uint8),
+                                       crop_plain=torch.zeros(2, 2, dtype=torch.int32), want_aug=False)
+
+
+def test_replicated_site_bookkeeping_errors_and_counters(built_lib):
+    """Host logic of the statistics-collection site that runs before any kernel: a running_mean shared by branches
+    whose second-moment buffers differ cannot be folded into one update (ValueError); BN branch counters advance
+    once per branch (utils/batch_norm.py:57-58) even though the site is evaluated once."""
+    import dwt_b200
+    rm, rv1, rv2 = torch.zeros(1, 8, 1, 1), torch.eye(4).repeat(2, 1, 1), torch.eye(4).repeat(2, 1, 1)
+    mods = [dwt_b200.WTransform2d(8, 4, running_m=rm, running_var=v).train() for v in (rv1, rv2, rv2)]
+    with pytest.raises(ValueError, match="paired"):
+        dwt_b200.DomainTripleNorm("whiten", 8, 4)(torch.randn(2, 8, 4, 4), mods, torch.ones(8, 1, 1), torch.zeros(8, 1, 1),
+                                                  replicated=True)
+    bm, bv = torch.zeros(8), torch.ones(8)
+    bns = [dwt_b200.BatchNorm2d(8, bm, bv, affine=False).train() for _ in range(3)]
+    with pytest.raises(built_lib.NativeError):          # CPU tensors: refused by the kernel call, after the bookkeeping
+        dwt_b200.DomainTripleNorm("bn", 8)(torch.randn(2, 8, 4, 4), bns, torch.ones(8, 1, 1), torch.zeros(8, 1, 1),
+                                           replicated=True)
+    assert [int(m.num_batches_tracked) for m in bns] == [1, 1, 1]
