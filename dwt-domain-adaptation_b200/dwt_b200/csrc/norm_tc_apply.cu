@@ -4,7 +4,7 @@
 //   bwd_apply   dx = A1 (dy - mean_M dy) + Bm (x - mean)        two input tensors
 //
 // Per 64-channel super-block the per-group matrices form one block-diagonal 64x64 matrix M, and a
-// [64 ch x 64 px] tile of the NCHW tensor is out = M * tile: a GEMM whose B operand is the tile exactly
+// [64 ch x 128 px] tile of the NCHW tensor is out = M * tile: a GEMM whose B operand is the tile exactly
 // as TMA lands it (rows = channels = K, pixels contiguous = MN-major), so nothing is transposed.
 // A single-pass TF32 product is NOT accurate enough here -- each output is one length-64 dot product
 // whose terms can cancel by the condition number of the covariance -- so both operands are split
@@ -16,7 +16,8 @@
 //           written per element;
 //   centring is linear, M (x - shift) = M x - M shift, and is applied as one constant per row at the end.
 //
-// CTA = 2 + 4 + 4 warps (one input, two CTAs per SM) or 2 + 8 + 8 warps (two inputs, one CTA per SM), persistent over a contiguous range of 64-pixel tiles of one (domain, super-block):
+// CTA = 2 + 8 + 8 warps, one per SM, persistent over a contiguous range of 128-pixel tiles of one (domain,
+// super-block); every input tensor of a tile is one STEP through the rings:
 //   warp 0     TMA producer into a RAW ring (4 boxes of 32 px x 64 ch per slot,
 //              SWIZZLE_128B_ATOM_32B: the only layout the tensor core takes for an MN-major tf32 operand)
 //   warp 1     MMA issuer (tcgen05.mma kind::tf32, M=128 N=128 K=8; A resident in TMEM, B MN-major), TMEM owner
