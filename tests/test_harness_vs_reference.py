@@ -53,3 +53,59 @@ def test_harness_equals_reference_model(monkeypatch):
     ref.eval(); mine.eval()
     with torch.no_grad():
         assert torch.allclose(ref(x), mine(x), atol=1e-4)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/utils"), reason="reference not mounted (GPU box)")
+def test_module_surface_is_the_references_own():
+    """Build-container check against the UNMODIFIED reference modules: attributes, buffer identity, state-dict keys
+    and initial values (same RNG stream), repr, checkpoint-version shim and every error text, string for string."""
+    import importlib.util
+    import warnings
+    warnings.filterwarnings("ignore")
+    from dwt_b200 import batch_norm as B, whitening as W
+
+    def load_ref(name):
+        spec = importlib.util.spec_from_file_location("ref_" + name, f"/root/reference/utils/{name}.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    def err(fn, *a):
+        try:
+            fn(*a)
+        except ValueError as e:
+            return str(e)
+        return None
+
+    RW, RB = load_ref("whitening"), load_ref("batch_norm")
+    for args in [dict(num_features=8, group_size=4), dict(num_features=8, group_size=16), dict(num_features=48, group_size=32),
+                 dict(num_features=8, group_size=4, running_m=torch.zeros(1, 8, 1, 1), running_var=torch.ones(2, 4, 4)),
+                 dict(num_features=8, group_size=4, running_m=torch.zeros(1, 8, 1, 1), running_var=torch.ones(2, 4, 4),
+                      track_running_stats=False, momentum=0.3, eps=1e-2, alpha=2)]:
+        a, r = W.WTransform2d(**args), RW.WTransform2d(**args)
+        for k in ["num_features", "momentum", "track_running_stats", "eps", "alpha", "group_size", "num_groups"]:
+            assert getattr(a, k) == getattr(r, k), (k, args)
+        assert a.running_m is args.get("running_m") and a.running_var is args.get("running_var")
+        assert list(a.state_dict()) == list(r.state_dict())
+        assert all(torch.equal(a.state_dict()[k], r.state_dict()[k].cpu()) for k in a.state_dict())
+        for bad in [torch.zeros(2, 8, 3), torch.zeros(2, args["num_features"], 3, 3)]:
+            check = lambda m: (m._check_input_dim(bad), m._check_group_size())      # noqa: E731
+            assert err(check, a) == err(check, r)
+    for cls in ("BatchNorm1d", "BatchNorm2d", "BatchNorm3d"):
+        for kw in [dict(affine=True), dict(affine=False), dict(affine=True, track_running_stats=False),
+                   dict(momentum=None, eps=1e-3)]:
+            torch.manual_seed(0)
+            a = getattr(B, cls)(6, torch.zeros(6), torch.ones(6), **kw)
+            torch.manual_seed(0)
+            r = getattr(RB, cls)(6, torch.zeros(6), torch.ones(6), **kw)
+            assert repr(a) == repr(r) and a._version == r._version
+            assert list(a.state_dict()) == list(r.state_dict())
+            assert all(torch.equal(a.state_dict()[k], r.state_dict()[k]) for k in a.state_dict())
+            assert [n for n, _ in a.named_parameters()] == [n for n, _ in r.named_parameters()]
+            assert [n for n, _ in a.named_buffers()] == [n for n, _ in r.named_buffers()]
+            for nd in range(2, 7):
+                x = torch.zeros(*([2, 6] + [3] * (nd - 2)))
+                assert err(a._check_input_dim, x) == err(r._check_input_dim, x), (cls, nd)
+            if kw.get("track_running_stats", True):
+                v1 = {k: v for k, v in a.state_dict().items() if "num_batches" not in k}
+                a.load_state_dict(v1)                             # pre-version-2 checkpoint: no counter
