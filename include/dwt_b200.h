@@ -19,6 +19,14 @@
  *   dwt_whiten_bwd   autograd through the above     utils/whitening.py:41-55
  *   dwt_bn_fwd/bwd   _BatchNorm.forward             utils/batch_norm.py:54-69
  *   dwt_mec_fwd_bwd  MinEntropyConsensusLoss.forward utils/consensus_loss.py:11-24
+ *   dwt_head_loss_fwd_bwd  the training loop's NLL + lambda*MEC   resnet50_dwt_mec_officehome.py:421-428
+ *   dwt_augment_pair the loader's two target views  resnet50_dwt_mec_officehome.py:481-492,526-542;
+ *                                                   utils/folder.py:127-147
+ *
+ * Threading: calls may come from any host thread (PyTorch runs backward on its own); the error text is
+ * per thread.  One process drives ONE device (the reference's and torchrun's model): kernel attributes
+ * (shared-memory opt-in, carve-out) and the TMA encoder are set up once per process, on the device that is
+ * current at the first call.  Every entry point may be captured into a CUDA graph.
  *
  * Tensor layout: activations are fp32, contiguous [n_domains * N, C, HW]
  * ("NCHW" with H*W flattened); domain d owns images [d*N, (d+1)*N).  The
