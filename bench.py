@@ -17,9 +17,16 @@ memory and the loss read back inside the timed region; `roofline` = the dominant
 kernel family against the measured HBM peak; `cpu_baseline` = the CPU port of the reference
 layers (oracle/torch_port.py, same harness model) timed on this box's host cores.
 
+At N = 1 the line also carries
+  `microbench`        BASELINE.json configs[1] (WTransform2d N=256 C=256 56x56 group_size=64, fwd+bwd: the TMA +
+                      tcgen05 kernels) with its own roofline, per-kernel table, CPU baseline and reference-on-GPU time;
+  `reference_on_gpu`  the reference's operator sequence (oracle/torch_port.py: stock ATen / cuBLAS / cuSOLVER / cuDNN
+                      ops, eager, torch's default math modes) on the SAME B200 for configs[2] -- what a user of the
+                      reference gets on this GPU today -- and the speed-up over it.
+
 --impl reference: the reference's own CPU path (no GPU): the same step with the reference's
 operator sequence on stock ATen CPU ops (oracle/torch_port.py), all host threads, a bounded sample.
---workload microbench: BASELINE.json configs[1] (WTransform2d N=256 C=256 56x56 gs=64 fwd+bwd).
+--workload microbench: only BASELINE.json configs[1] (WTransform2d N=256 C=256 56x56 gs=64 fwd+bwd).
 """
 from __future__ import annotations
 
@@ -192,7 +199,9 @@ def train_step(model, mec, opt, images, labels, sync=None, head=None):
 
 # ----------------------------------------------------------------------------------------- arms
 def run_reference(args):
-    """The reference's CPU path: harness model + CPU port of the reference layers, all host threads."""
+    """The reference's CPU path: harness model + CPU port of the reference layers, all host threads.
+    Under torchrun only rank 0 works (one host, one set of cores): its images/s IS the whole-job figure of the
+    CPU arm whatever --gpus says -- the host does not get faster when the GPU arm adds ranks."""
     import oracle.torch_port as port
     from harness.synth import synth_batch
     rank = int(os.environ.get("RANK", "0"))
@@ -200,8 +209,10 @@ def run_reference(args):
         return
     cores = host_cores()
     torch.set_num_threads(cores)
-    per_domain = args.cpu_per_domain
     dev = torch.device("cpu")
+    if args.workload == "microbench":
+        return run_reference_micro(args, port, cores)
+    per_domain = args.cpu_per_domain
     model = build_model(port, dev, "modules")
     opt = make_optimizer(model)
     mec = port.MinEntropyConsensusLoss(NUM_CLASSES, dev)
@@ -213,15 +224,51 @@ def run_reference(args):
         train_step(model, mec, opt, images, labels)
     dt = (time.perf_counter() - t0) / args.steps
     val = 3 * per_domain / dt
-    sample = f"{args.steps} steps of {3 * per_domain} images (3x{per_domain}), same model/step as the GPU arm"
+    sample = (f"{args.steps} steps of {3 * per_domain} images (3x{per_domain}; the GPU arm steps 3x{args.per_domain} per rank), "
+              "same model / loss / optimizer step")
     print(json.dumps({
         "impl": "reference", "metric": "ResNet-50-DWT images/sec fwd+bwd", "value": val, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, per_domain=per_domain, site_mode="modules"),
+        "whole_job": "one host: rank 0 alone runs; images/s of this host, independent of --gpus",
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_reference_micro(args, port, cores):
+    """configs[1] on the host cores: the reference layer's operator sequence, N scaled down (the full N=256 tensor
+    needs ~8 GB of autograd-saved copies and ~2 s per iteration; BASELINE.md §4 allows scaling N only)."""
+    N, C, H, gs = args.micro_cpu_n, 256, 56, args.micro_gs
+    torch.manual_seed(0)
+    mix = torch.randn(C, C) / C ** 0.5 + torch.eye(C)
+    x = (torch.einsum("dc,nchw->ndhw", mix, torch.randn(N, C, H, H)) + 2.0).contiguous().requires_grad_(True)
+    dy = torch.randn(N, C, H, H)
+    m = port.WTransform2d(C, gs).train()
+
+    def step():
+        torch.autograd.grad(m(x), x, dy)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    k = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        step()
+    dt = (time.perf_counter() - t0) / k
+    # the layer is linear in N: report the time scaled to the full-size tensor next to the measured one
+    print(json.dumps({
+        "impl": "reference", "metric": "WTransform2d fwd+bwd microbench", "value": 1.0 / (dt * args.micro_n / N),
+        "unit": "iterations/s", "n_gpus": args.gpus, "steps": k, "warmup": args.warmup, "ms_per_step": dt * 1e3 * args.micro_n / N,
+        "measured_ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"WTransform2d N={args.micro_n} C={C} H=W={H} group_size={gs} fwd+bwd",
+                   "measured_at": f"N={N} (1/{args.micro_n // N} of the batch axis), time scaled by {args.micro_n // N}"},
+        "cpu_baseline": {"value": 1.0 / (dt * args.micro_n / N), "unit": "iterations/s", "cores": torch.get_num_threads(),
+                         "kind": "port", "sample": f"{k} iterations at N={N}, scaled x{args.micro_n // N} to N={args.micro_n}"},
+        "e2e": {"value": 1.0 / (dt * args.micro_n / N), "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
@@ -234,18 +281,73 @@ def workload_config(args, per_domain, site_mode):
             "launch": "CUDA-graph replay of the whole step" if getattr(args, "cuda_graph", False) and getattr(args, "impl", "ours") == "ours" else "eager"}
 
 
-def cpu_baseline(args):
-    """Bounded CPU sample on rank 0: a few steps of the CPU port at a small per-domain batch."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
-           "--cpu-per-domain", str(args.cpu_per_domain)]
+def cpu_baseline(args, workload="resnet"):
+    """Bounded CPU sample on rank 0: a few steps of the CPU port (configs[2] at a small per-domain batch, configs[1] at
+    a fraction of N), in a subprocess that cannot see the GPU."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2" if workload == "resnet" else "3",
+           "--warmup", "1", "--workload", workload, "--cpu-per-domain", str(args.cpu_per_domain),
+           "--per-domain", str(args.per_domain), "--micro-n", str(args.micro_n), "--micro-cpu-n", str(args.micro_cpu_n),
+           "--micro-gs", str(args.micro_gs)]
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="0", WORLD_SIZE="1")
     for k in ("LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
         env.pop(k, None)
+    unit = "images/s" if workload == "resnet" else "iterations/s"
     try:
         out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600).stdout.strip().splitlines()
         return json.loads(out[-1])["cpu_baseline"]
     except Exception as e:                                   # the GPU number must not die with the CPU leg
-        return {"value": None, "unit": "images/s", "cores": host_cores(), "kind": "port", "sample": f"failed: {e}"}
+        return {"value": None, "unit": unit, "cores": host_cores(), "kind": "port", "sample": f"failed: {e}"}
+
+
+# ------------------------------------------------------------------------- reference on the same GPU
+def reference_on_gpu_resnet(args, device):
+    """configs[2] with the reference's operator sequence on this GPU (oracle/torch_port.py: x.mean / bmm /
+    linalg.cholesky / inverse / grouped conv2d / F.batch_norm / split-cat-affine-relu composition, autograd backward),
+    eager, NCHW, torch's default math modes (fp32 matmul, cuDNN TF32 convolutions -- the same convolutions as our
+    arm).  /root/reference itself cannot travel to the GPU box; the port restates utils/whitening.py:37-61,
+    utils/batch_norm.py:54-69, utils/consensus_loss.py:11-24 op for op (tests/test_oracle_vs_golden.py pins it)."""
+    import oracle.torch_port as port
+    from harness.synth import synth_batch
+    B = args.per_domain
+    model = build_model(port, device, "modules")
+    opt = make_optimizer(model)
+    mec = port.MinEntropyConsensusLoss(NUM_CLASSES, device)
+    images, labels = synth_batch(seed=100, per_domain=B)
+    images, labels = images.to(device), labels.to(device)
+
+    def step():
+        train_step(model, mec, opt, images, labels)
+
+    for _ in range(3):
+        step()
+    k = max(3, min(args.steps, 10))
+    ms = timed_loop(step, k, device, False)
+    del model, opt
+    return {"value": 3 * B * k / (ms / 1e3), "unit": "images/s", "ms_per_step": ms / k, "steps": k,
+            "impl": "oracle/torch_port.py on cuda (stock ATen ops, eager, NCHW, matmul fp32, cuDNN TF32 convs)",
+            "per_domain_batch": B}
+
+
+def reference_on_gpu_micro(args, device):
+    """configs[1] with the reference layer's operator sequence on this GPU (utils/whitening.py:41-59)."""
+    import oracle.torch_port as port
+    N, C, H, gs = args.micro_n, 256, 56, args.micro_gs
+    torch.manual_seed(0)
+    mix = torch.randn(C, C, device=device) / C ** 0.5 + torch.eye(C, device=device)
+    x = (torch.einsum("dc,nchw->ndhw", mix, torch.randn(N, C, H, H, device=device)) + 2.0).contiguous().requires_grad_(True)
+    dy = torch.randn(N, C, H, H, device=device)
+    m = port.WTransform2d(C, gs).to(device).train()
+
+    def step():
+        torch.autograd.grad(m(x), x, dy)
+
+    for _ in range(3):
+        step()
+    k = max(3, min(args.steps, 10))
+    ms = timed_loop(step, k, device, False)
+    return {"value": k / (ms / 1e3), "unit": "iterations/s", "ms_per_step": ms / k, "steps": k,
+            "impl": "oracle/torch_port.py WTransform2d on cuda (mean, transposing copy, bmm, linalg.cholesky, inverse, "
+                    "grouped conv2d; autograd backward), eager, fp32"}
 
 
 def timed_loop(step_fn, steps, device, distributed):
@@ -306,7 +408,14 @@ def run_ours(args):
     _native.lib()                                           # fail loudly if the extension is missing
 
     if args.workload == "microbench":
-        return run_microbench(args, device, rank)
+        rec = run_microbench(args, device)
+        if rank == 0:
+            if args.cpu_baseline:
+                rec["cpu_baseline"] = cpu_baseline(args, "microbench")
+            rec["reference_on_gpu"] = reference_on_gpu_micro(args, device)
+            rec["vs_reference_gpu"] = rec["value"] / rec["reference_on_gpu"]["value"]
+            print(json.dumps(rec))
+        return
 
     nhwc = args.memory_format == "nhwc"
     model = build_model(dwt_b200, device, args.site_mode, channels_last=nhwc)
@@ -469,10 +578,12 @@ def run_ours(args):
     dom = max((k for k in fams if fams[k]["bytes"] > 0), key=lambda k: fams[k]["ms"], default=None)
     roof = None
     traffic_tab = {}
-    try:
-        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
-    except Exception:
-        pass
+    for name in ("traffic_r02.json", "traffic_r01.json"):
+        try:
+            traffic_tab = json.load(open(os.path.join(ROOT, "profiles", name)))
+            break
+        except Exception:
+            pass
     if dom is not None:
         f = fams[dom]
         ratio = traffic_tab.get("traffic_over_algorithmic", {}).get(dom)
@@ -486,6 +597,15 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": f["bytes"] / f["launches"],
                 "all_norm_kernels_share_of_step": sum(v["ms"] for v in fams.values()) / ms_eager,
                 "timed_in": "eager pass of this run (launches bracketed by CUDA events; graph replay hides them)"}
+        byte_fams = {k: v for k, v in fams.items() if v["bytes"] > 0 and k != "head_loss"}
+        tot_b, tot_ms = sum(v["bytes"] for v in byte_fams.values()), sum(v["ms"] for v in fams.values() if v is not None)
+        worst = min(byte_fams, key=lambda k: byte_fams[k]["gbs"])
+        # every hand-written norm launch of the step, finalize launches included in the time: the path as a whole.
+        # Algorithmic bytes over time can exceed the DRAM peak: the kernels sweep the tensor in the order that finds
+        # the producer's last ~100 MB still in L2 (norm_cl.cu), and those bytes never reach HBM.
+        roof["norm_path"] = {"achieved": tot_b / (tot_ms * 1e-3) / 1e9, "frac": tot_b / (tot_ms * 1e-3) / 1e9 / peak,
+                             "algorithmic_gb_per_step": tot_b / args.steps / 1e9, "ms_per_step": tot_ms / args.steps,
+                             "worst_family": worst, "worst_frac": byte_fams[worst]["gbs"] / peak}
     out = {
         "metric": "ResNet-50-DWT images/sec fwd+bwd", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -500,12 +620,37 @@ def run_ours(args):
     }
     if args.cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args)
+    out["status_word"] = _native.status_all(device)            # 0: no kernel reported a failure during the run
+    if not distributed and args.extras:
+        # free the step's graph, model and activations before the two side measurements
+        del graph, static_loss, model, net, opt
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            ref = reference_on_gpu_resnet(args, device)
+            ref["speedup_value"] = value / ref["value"]
+            ref["speedup_e2e"] = e2e / ref["value"]
+            out["reference_on_gpu"] = ref
+        except Exception as e:
+            out["reference_on_gpu"] = {"value": None, "error": f"{type(e).__name__}: {e}"}
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            mb = run_microbench(args, device)
+            if args.cpu_baseline:
+                mb["cpu_baseline"] = cpu_baseline(args, "microbench")
+            mb["reference_on_gpu"] = reference_on_gpu_micro(args, device)
+            mb["vs_reference_gpu"] = mb["value"] / mb["reference_on_gpu"]["value"]
+            out["microbench"] = mb
+        except Exception as e:
+            out["microbench"] = {"value": None, "error": f"{type(e).__name__}: {e}"}
     print(json.dumps(out))
     finish(distributed, device)
 
 
-def run_microbench(args, device, rank):
-    """BASELINE.json configs[1]: WTransform2d N=256 C=256 H=W=56 group_size=64, fwd+bwd."""
+def run_microbench(args, device):
+    """BASELINE.json configs[1]: WTransform2d N=256 C=256 H=W=56 group_size=64, fwd+bwd -> record (dict)."""
     import dwt_b200
     from dwt_b200 import _native
     N, C, H, gs = args.micro_n, 256, 56, args.micro_gs
@@ -516,15 +661,17 @@ def run_microbench(args, device, rank):
     x = (torch.einsum("dc,nchw->ndhw", mix, torch.randn(N, C, H, H, device=device)) + 2.0).contiguous().requires_grad_(True)
     dy = torch.randn(N, C, H, H, device=device)
     m = dwt_b200.WTransform2d(C, gs).to(device).train()
+    steps = max(args.steps, 20)                      # >= 20 iterations after >= 5 warm-ups
+    warm = max(args.warmup, 5)
 
     def step():
         y = m(x)
         torch.autograd.grad(y, x, dy)
 
-    for _ in range(args.warmup):
+    for _ in range(warm):
         step()
     graph = None
-    if args.cuda_graph:                              # the four launches as one graph: no host time between them
+    if args.cuda_graph:                              # the launches as one graph: no host time between them
         side = torch.cuda.Stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
@@ -536,37 +683,42 @@ def run_microbench(args, device, rank):
         graph.replay()
     with ClockSampler(device.index) as clocks:
         _native.profile_begin()
-        eager_ms = timed_loop(step, args.steps, device, False)
+        eager_ms = timed_loop(step, steps, device, False)
         prof = _native.by_family(_native.profile_end())
-        ms = timed_loop(graph.replay, args.steps, device, False) if graph is not None else eager_ms
-    if rank != 0:
-        return
+        ms = timed_loop(graph.replay, steps, device, False) if graph is not None else eager_ms
     peak, peak_src = measured_peaks()
     elems = N * C * H * H
     total_bytes = 32.0 * elems                       # 12 B/elem forward + 20 B/elem backward
-    fams = {k: dict(v, gbs=v["bytes"] / (v["ms"] * 1e-3) / 1e9, us_per_launch=1e3 * v["ms"] / v["launches"])
+    fams = {k: dict(v, gbs=(v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["bytes"] > 0 else None),
+                    us_per_launch=1e3 * v["ms"] / v["launches"], frac=(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak if v["bytes"] > 0 else None))
             for k, v in prof.items() if v["ms"] > 0}
-    gbs = total_bytes * args.steps / (ms * 1e-3) / 1e9
+    gbs = total_bytes * steps / (ms * 1e-3) / 1e9
     ratio, ratio_src = None, None
-    try:
-        tab = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))["tensor_core_path"]
-        if gs >= 8:
-            ratio, ratio_src = tab["traffic_over_algorithmic"]["fwd+bwd (all launches)"], tab["source"]
-    except Exception:
-        pass
-    print(json.dumps({
-        "metric": "WTransform2d fwd+bwd microbench", "value": args.steps / (ms * 1e-3), "unit": "iterations/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "eager_ms_per_step": eager_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    for name in ("traffic_r02.json", "traffic_r01.json"):
+        try:
+            tab = json.load(open(os.path.join(ROOT, "profiles", name)))["tensor_core_path"]
+            if gs >= 8:
+                ratio, ratio_src = tab["traffic_over_algorithmic"]["fwd+bwd (all launches)"], tab["source"]
+            break
+        except Exception:
+            pass
+    tc = gs >= 8
+    return {
+        "metric": "WTransform2d fwd+bwd microbench", "value": steps / (ms * 1e-3), "unit": "iterations/s",
+        "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
+        "eager_ms_per_step": eager_ms / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (tf32 tensor-core contraction with hi/lo split operands, split-tf32 apply, fp32 accumulate)" if tc else "f32",
+        "data": "synthetic",
         "config": {"workload": f"WTransform2d N={N} C={C} H=W={H} group_size={gs} fwd+bwd",
                    "l2": f"tensor of {elems * 4 / 1e6:.0f} MB > 126 MB L2",
                    "launch": "cuda-graph replay" if graph is not None else "eager"},
-        "roofline": {"bound": "hbm", "kernel": "fwd+bwd (4 launches)", "achieved": gbs, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "fwd+bwd (all launches of the layer)", "achieved": gbs, "peak": peak, "unit": "GB/s",
                      "frac": gbs / peak, "traffic": ratio * total_bytes if ratio else None, "traffic_source": ratio_src,
                      "algorithmic_bytes_per_step": total_bytes, "peak_source": peak_src},
-        "kernels": fams, "clocks": clocks.summary(),
-    }))
+        "kernels": fams, "clocks": clocks.summary(), "gpu_launches": int(sum(v["launches"] for v in prof.values()) // steps),
+        "status_word": _native.status_all(device),
+    }
 
 
 def main():
@@ -580,7 +732,11 @@ def main():
     ap.add_argument("--site-mode", choices=["fused", "modules"], default="fused")
     ap.add_argument("--memory-format", choices=["nchw", "nhwc"], default="nhwc",
                     help="activation layout of the GPU arm (nhwc = torch.channels_last end to end)")
-    ap.add_argument("--cpu-per-domain", type=int, default=4)
+    ap.add_argument("--cpu-per-domain", type=int, default=16,
+                    help="per-domain batch of the CPU arm (a bounded sample of the GPU arm's 3x64-image step)")
+    ap.add_argument("--micro-cpu-n", type=int, default=32, help="batch size of the CPU leg of the microbench (N scaled down)")
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="skip the microbench and reference-on-GPU sub-records of the default N=1 line")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
                     help="time the eager step instead of a CUDA-graph replay of it")

@@ -5,6 +5,7 @@ the reference's ``utils/`` and the reference scripts' ``import whitening`` / ``i
 / ``import consensus_loss`` resolve to the shims next to this package, i.e. to these classes.
 """
 from . import _native
+from ._native import NotPositiveDefiniteError, check_status, raise_on_status
 from .augment import PairedAugment, draw_params
 from .batch_norm import BatchNorm1d, BatchNorm2d, BatchNorm3d
 from .consensus_loss import HeadLoss, MinEntropyConsensusLoss
@@ -12,4 +13,5 @@ from .fused import DomainTripleNorm
 from .whitening import WTransform2d
 
 __all__ = ["WTransform2d", "BatchNorm1d", "BatchNorm2d", "BatchNorm3d", "MinEntropyConsensusLoss",
-           "DomainTripleNorm", "HeadLoss", "PairedAugment", "draw_params", "_native"]
+           "DomainTripleNorm", "HeadLoss", "PairedAugment", "draw_params", "raise_on_status", "check_status",
+           "NotPositiveDefiniteError", "_native"]

@@ -13,12 +13,13 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdwt_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_DOMAINS = 4
 MAX_GROUP_SIZE = 64
 MODE_TRAIN, MODE_EVAL = 0, 1
 EPI_NONE, EPI_AFFINE, EPI_RELU, EPI_RESIDUAL = 0, 1, 2, 4
 LAYOUT_NHWC = 0x100
+STATUS_NOT_PD, STATUS_BAD_LABEL = 1, 2
 
 _c_float_p = ctypes.c_void_p
 _PtrArray = ctypes.c_void_p * MAX_DOMAINS
@@ -30,25 +31,26 @@ _SIGNATURES = {
     "dwt_whiten_fwd": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                       ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
-                                      _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, _c_float_p, _c_float_p,
-                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+                                      _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_int, _c_float_p,
+                                      _c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "dwt_whiten_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
-                                      _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int, _c_float_p,
-                                      _c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+                                      _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p, _c_float_p,
+                                      ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t,
+                                      ctypes.c_void_p]),
     "dwt_bn_fwd": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                   ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int,
                                   ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), _c_float_p,
-                                  _c_float_p, _c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p,
-                                  ctypes.c_size_t, ctypes.c_void_p]),
+                                  _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_int, _c_float_p, _c_float_p,
+                                  ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "dwt_bn_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                   ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
-                                  ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t,
-                                  ctypes.c_void_p]),
+                                  ctypes.c_void_p, _c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p,
+                                  ctypes.c_size_t, ctypes.c_void_p]),
     "dwt_mec_fwd_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, _c_float_p,
                                        _c_float_p, _c_float_p, ctypes.c_void_p]),
     "dwt_head_loss_fwd_bwd": (ctypes.c_int, [_c_float_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_float,
-                                             _c_float_p, _c_float_p, ctypes.c_void_p]),
+                                             _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
     "dwt_augment_pair": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_float_p,
                                         ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _c_float_p,
@@ -180,8 +182,73 @@ def workspace(device, n, c, hw, gs, nd):
 
 
 def status(device=None) -> int:
-    """Device status word of the current stream's workspace (syncs).  Bit 0: a covariance was
-    not positive definite (the reference raises from torch.cholesky at that point)."""
+    """Device status word of the current stream's workspace (syncs).  Bit 0 (STATUS_NOT_PD): a covariance was
+    not positive definite (the reference raises from torch.cholesky at that point); bit 1 (STATUS_BAD_LABEL): the
+    head loss met a label outside [0, K) other than -100 (F.nll_loss device-asserts)."""
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     buf = _workspaces.get((device.index, torch.cuda.current_stream(device).cuda_stream))
     return 0 if buf is None else int(buf[:4].view(torch.int32).item())
+
+
+def status_all(device=None) -> int:
+    """OR of the status words of every stream's workspace on the device (syncs): CUDA-graph capture runs on its own
+    stream and therefore on its own workspace."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    torch.cuda.synchronize(device)
+    st = 0
+    for (idx, _), buf in _workspaces.items():
+        if idx == device.index:
+            st |= int(buf[:4].view(torch.int32).item())
+    return st
+
+
+def status_ptr(device):
+    """Device address of the current stream's status word (the head-loss kernel ORs its bit in there)."""
+    return ctypes.c_void_p(workspace(device, 1, 4, 1, 1, 1).data_ptr())
+
+
+def clear_status(device=None) -> None:
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    buf = _workspaces.get((device.index, torch.cuda.current_stream(device).cuda_stream))
+    if buf is not None:
+        buf[:4].zero_()
+
+
+class NotPositiveDefiniteError(torch.linalg.LinAlgError):
+    """What the reference's torch.cholesky raises at utils/whitening.py:53, raised late: the kernels never sync the
+    host, so the failure is seen at the next poll (raise_on_status) or explicit check_status() call."""
+
+
+_poll = {"every": 0, "count": 0}
+
+
+def raise_on_status(every: int = 1) -> None:
+    """Opt-in failure surfacing: every `every`-th layer call (forward of a whitening / BN / fused-site / head-loss
+    layer) reads the status word -- one 4-byte device->host copy, i.e. a host sync -- and raises.  every=0 turns the
+    polling off again (the default: the hot path never syncs).  Not for use while capturing a CUDA graph."""
+    _poll["every"], _poll["count"] = max(0, int(every)), 0
+
+
+def check_status(device=None) -> None:
+    """Read the status word now (syncs) and raise if a kernel reported a failure; clears the word."""
+    st = status(device)
+    if st == 0:
+        return
+    clear_status(device)
+    if st & STATUS_NOT_PD:
+        raise NotPositiveDefiniteError(
+            "cholesky: a whitening covariance was not positive definite (status word bit 0; the reference raises "
+            "from torch.cholesky, utils/whitening.py:53); the affected group's output is NaN and its running-"
+            "statistics update was skipped")
+    if st & STATUS_BAD_LABEL:
+        raise IndexError("head loss: a label was outside [0, num_classes) and is not ignore_index=-100 "
+                         "(F.nll_loss asserts here); the row was dropped")
+    raise NativeError(f"unknown status bits {st:#x}")
+
+
+def poll_status(device) -> None:
+    if _poll["every"]:
+        _poll["count"] += 1
+        if _poll["count"] >= _poll["every"]:
+            _poll["count"] = 0
+            check_status(device)

@@ -3,6 +3,7 @@
 // allocation, no CPU fallback.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -114,21 +115,35 @@ int tc_apply_ctas(const dwt::Geom& g, int per_sm, int tile_px) {
   return n < 1 ? 1 : n;
 }
 
-// channels-last launch shaping: CTAs per (domain, column slab) for reductions (one wave) and elementwise kernels
-struct ClPlan { int nred, new_, S, gridy; };
-ClPlan cl_plan(const dwt::Geom& g, int slots_per_sm) {
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// channels-last launch shaping.  Every kernel is ONE wave of persistent CTAs sweeping 32-row chunks (norm_cl.cu):
+// grid.x CTAs per (domain, column slab), grid.y slabs, grid.z = D domains side by side.  (grid.z = 1 -- all CTAs
+// sweeping the domains one after the other, so that the whole grid moves through the tensor as a single window --
+// was measured on the B200 step and is slower: 31.8 vs 31.5 ms, three times the partial rows for no extra L2 hits;
+// the kernels still accept it, DWT_CL_SEQ_MB=<tensor MB threshold> turns it on for experiments.)
+struct ClPlan { int nred, new_, S, gridy, gz_red, gz_ew; };
+ClPlan cl_plan(const dwt::Geom& g, int slots_red, int slots_ew, int unroll_red, int unroll_ew) {
+  static const int seq_mb = env_int("DWT_CL_SEQ_MB", 1 << 30);  // experiment switch, off by default
   const int C4 = g.C / 4, CW = C4 < 256 ? C4 : 256, rpi = 256 / CW, gridy = C4 / CW;
   const long long rows = (long long)g.N * g.HW;
+  const double mbytes = 4.0 * (double)g.D * (double)rows * (double)g.C / 1048576.0;
+  const bool seq = g.D > 1 && mbytes >= (double)seq_mb;
   ClPlan p;
   p.gridy = gridy;
-  long long by_work = rows / ((long long)rpi * 16);      // >= 16 rows per thread (two load batches)
-  if (by_work < 1) by_work = 1;
-  int cap = slots_per_sm * sm_count() / (gridy * g.D);
-  if (cap < 1) cap = 1;
-  p.nred = (int)(by_work < cap ? by_work : cap);
-  long long by_work_ew = rows / ((long long)rpi * 8);
-  if (by_work_ew < 1) by_work_ew = 1;
-  p.new_ = (int)(by_work_ew < 4LL * cap ? by_work_ew : 4LL * cap);
+  p.gz_red = p.gz_ew = seq ? 1 : g.D;
+  auto shape = [&](int slots, int unroll, int gz) {
+    long long by_work = rows / ((long long)rpi * unroll * 2);      // >= two load batches per CTA and domain
+    if (by_work < 1) by_work = 1;
+    int cap = slots * sm_count() / (gridy * gz);
+    if (cap < 1) cap = 1;
+    return (int)(by_work < cap ? by_work : cap);
+  };
+  p.nred = shape(slots_red, unroll_red, p.gz_red);
+  p.new_ = shape(slots_ew, unroll_ew, p.gz_ew);
   p.S = p.nred < 8 ? p.nred : 8;
   return p;
 }
@@ -168,6 +183,7 @@ struct Workspace {
   float* gram;        // [D*SB*(64*64+64)]  reduced moments of the tensor-core contraction
   float* shift;       // [D*SB*64]          pilot shift of every channel
   float* red;         // [D*8*W]            channels-last path: split-reduced partial moments
+  int* bad;           // [D*G]              per (domain, group): batch covariance not positive definite
   size_t bytes;
 };
 
@@ -199,7 +215,8 @@ Workspace carve(void* base, int64_t C, int GS, int D) {
   size_t red_floats = 1;
   if (dwt::cl_supports((int)C, GS)) {                      // channels-last path: per-CTA rows of C/4-column vectors
     const size_t W = (size_t)dwt::cl_bwd_width((int)C, GS);
-    const size_t cl = ((size_t)3 * sm_count() + 4 * D) * W;
+    const int C4 = (int)C / 4, gridy = C4 <= 256 ? 1 : C4 / 256;
+    const size_t cl = (size_t)D * (3 * sm_count() / gridy + 1) * W;     // one row per (domain, CTA of grid.x)
     if (cl > partial_floats) partial_floats = cl;
     red_floats = (size_t)D * 8 * W;
   }
@@ -211,6 +228,7 @@ Workspace carve(void* base, int64_t C, int GS, int D) {
   const size_t SBn = (size_t)((C + 63) / 64);
   w.gram = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * SBn * (64 * 64 + 64)));
   w.shift = reinterpret_cast<float*>(b + take(sizeof(float) * (size_t)D * SBn * 64));
+  w.bad = reinterpret_cast<int*>(b + take(sizeof(int) * (size_t)D * G));
   w.bytes = off;
   return w;
 }
@@ -272,8 +290,9 @@ int make_plan(Plan& p, KernelKind reduce_kind, KernelKind ew_kind, const void* a
 
 int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, int GS, int D, int mode, float a,
                     float b, float momentum, float unbias, int update_running, float* const* rmean,
-                    float* const* rcov, const float* gamma, const float* beta, const float* residual, int epi,
-                    float* save_mean, float* save_w, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    float* const* rcov, const float* gamma, const float* beta, const float* residual,
+                    uint8_t* relu_mask, int epi, float* save_mean, float* save_w, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
   const bool nhwc = (mode & DWT_LAYOUT_NHWC) != 0;
   mode &= 0xFF;
   Plan p;
@@ -287,6 +306,8 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
   if ((epi & DWT_EPI_AFFINE) && (!gamma || !beta)) return fail(DWT_E_INVALID, "AFFINE epilogue needs gamma and beta");
   if ((epi & DWT_EPI_RESIDUAL) && ((epi & 3) != 3 || !residual)) return fail(DWT_E_INVALID, "RESIDUAL epilogue needs AFFINE|RELU and a residual tensor");
   if ((epi & DWT_EPI_RESIDUAL) && (uintptr_t)residual % 16 != 0) return fail(DWT_E_INVALID, "residual must be 16-byte aligned");
+  if (relu_mask && !((epi & DWT_EPI_RESIDUAL) && nhwc))
+    return fail(DWT_E_UNSUPPORTED, "the ReLU byte map is written by the channels-last RESIDUAL epilogue only");
   if (epi != 0 && !p.small)
     return fail(DWT_E_UNSUPPORTED, "fused gamma/beta/ReLU epilogue is built for group_size 1, 2, 4 (got %d)", GS);
   const bool need_running = (mode == DWT_MODE_EVAL) || update_running;
@@ -305,7 +326,7 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
   fin.update_running = (mode == DWT_MODE_TRAIN) ? update_running : 0;
   fin.save_mean = save_mean; fin.save_w = save_w; fin.save_cov = w.save_cov;
   for (int d = 0; d < D; ++d) { fin.rmean[d] = need_running ? rmean[d] : nullptr; fin.rcov[d] = need_running ? rcov[d] : nullptr; }
-  fin.dom_counter = w.dom_counter; fin.status = w.status;
+  fin.dom_counter = w.dom_counter; fin.status = w.status; fin.bad = w.bad;
   if (need_running && D > 1) {
     bool all_same = true, all_distinct = true;
     for (int d = 1; d < D; ++d) {
@@ -318,11 +339,11 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
 
   const double E = 4.0 * (double)D * (double)N * (double)C * (double)HW;   // bytes of one activation tensor
   if (nhwc) {
-    const ClPlan cp = cl_plan(p.gm, 3);
+    const ClPlan cp = cl_plan(p.gm, 3, 3, 8, (epi & DWT_EPI_RESIDUAL) ? 4 : 8);
     if (mode == DWT_MODE_TRAIN) {
       {
         Launch l("cl_stats", &p.gm, E, st);
-        dwt::cl_stats(x, p.gm, cp.nred, w.partial, w.shift, st);
+        dwt::cl_stats(x, p.gm, cp.nred, cp.gz_red, w.partial, w.shift, st);
       }
       if (int rc = check_launch("channels-last statistics kernel")) return rc;
       Launch l("cl_fwd_finalize", &p.gm, 0.0, st);
@@ -334,8 +355,8 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
     }
     if (int rc = check_launch("channels-last finalize kernel")) return rc;
     {
-      Launch l("cl_apply", &p.gm, ((epi & DWT_EPI_RESIDUAL) ? 3 : 2) * E, st);
-      dwt::cl_apply(x, y, p.gm, cp.new_, epi, save_mean, save_w, gamma, beta, residual, st);
+      Launch l("cl_apply", &p.gm, ((epi & DWT_EPI_RESIDUAL) ? (relu_mask ? 3.0625 : 3.0) : 2.0) * E, st);
+      dwt::cl_apply(x, y, p.gm, cp.new_, cp.gz_ew, epi, save_mean, save_w, gamma, beta, residual, relu_mask, st);
     }
     return check_launch("channels-last apply kernel");
   }
@@ -373,8 +394,8 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
 
 int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int64_t C, int64_t HW, int GS, int D,
                     int mode, float a, const float* save_mean, const float* save_w, const float* gamma,
-                    const float* beta, int epi, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
-                    cudaStream_t st) {
+                    const float* beta, const uint8_t* relu_mask, float* dresidual, int epi, float* dgamma,
+                    float* dbeta, void* ws, size_t ws_bytes, cudaStream_t st) {
   const bool nhwc = (mode & DWT_LAYOUT_NHWC) != 0;
   mode &= 0xFF;
   Plan p;
@@ -386,7 +407,15 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
   if (mode != DWT_MODE_TRAIN && mode != DWT_MODE_EVAL) return fail(DWT_E_INVALID, "bad mode %d", mode);
   if ((epi & DWT_EPI_RELU) && !(epi & DWT_EPI_AFFINE)) return fail(DWT_E_INVALID, "RELU epilogue needs AFFINE");
   if ((epi & DWT_EPI_AFFINE) && (!gamma || !beta)) return fail(DWT_E_INVALID, "AFFINE epilogue needs gamma and beta");
-  if (epi & DWT_EPI_RESIDUAL) return fail(DWT_E_INVALID, "backward of a RESIDUAL forward: pass dout already masked by (out > 0), epilogue AFFINE");
+  if (epi & DWT_EPI_RESIDUAL) {
+    // backward of out = relu(z + residual): the ReLU mask comes from the byte map the forward wrote
+    if (!nhwc || !relu_mask || (epi & 3) != 3)
+      return fail(DWT_E_INVALID, "backward of a RESIDUAL forward needs the channels-last layout, AFFINE|RELU and the forward's "
+                                 "ReLU byte map (or pass dout already masked by (out > 0) with epilogue AFFINE)");
+    if (dresidual && (uintptr_t)dresidual % 16 != 0) return fail(DWT_E_INVALID, "dresidual must be 16-byte aligned");
+  } else if (relu_mask || dresidual) {
+    return fail(DWT_E_INVALID, "relu_mask / dresidual belong to the RESIDUAL epilogue");
+  }
   if ((dgamma == nullptr) != (dbeta == nullptr)) return fail(DWT_E_INVALID, "dgamma and dbeta go together");
   if (epi != 0 && !p.small)
     return fail(DWT_E_UNSUPPORTED, "fused gamma/beta/ReLU epilogue is built for group_size 1, 2, 4 (got %d)", GS);
@@ -406,11 +435,12 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
   const bool need_reduce = (mode == DWT_MODE_TRAIN) || (fin.dgamma != nullptr);
   const double E = 4.0 * (double)D * (double)N * (double)C * (double)HW;
   if (nhwc) {
-    const ClPlan cp = cl_plan(p.gm, 2);
+    const ClPlan cp = cl_plan(p.gm, 2, 2, 4, 4);
+    const bool masked = (epi & DWT_EPI_RESIDUAL) != 0;
     if (need_reduce) {
       {
-        Launch l("cl_bwd_reduce", &p.gm, 2 * E, st);
-        dwt::cl_bwd_reduce(x, dout, p.gm, cp.nred, epi, save_mean, save_w, gamma, beta, w.partial, st);
+        Launch l("cl_bwd_reduce", &p.gm, (masked ? 2.0625 : 2.0) * E, st);
+        dwt::cl_bwd_reduce(x, dout, p.gm, cp.nred, cp.gz_red, epi, save_mean, save_w, gamma, beta, relu_mask, w.partial, st);
       }
       if (int rc = check_launch("channels-last backward reduction kernel")) return rc;
       Launch l("cl_bwd_finalize", &p.gm, 0.0, st);
@@ -422,8 +452,8 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
     }
     if (int rc = check_launch("channels-last backward finalize kernel")) return rc;
     {
-      Launch l("cl_bwd_apply", &p.gm, 3 * E, st);
-      dwt::cl_bwd_apply(x, dout, dx, p.gm, cp.new_, epi, w.coef, save_mean, save_w, gamma, beta, st);
+      Launch l("cl_bwd_apply", &p.gm, (masked ? (dresidual ? 4.0625 : 3.0625) : 3.0) * E, st);
+      dwt::cl_bwd_apply(x, dout, dx, p.gm, cp.new_, cp.gz_ew, epi, w.coef, save_mean, save_w, gamma, beta, relu_mask, dresidual, st);
     }
     return check_launch("channels-last backward apply kernel");
   }
@@ -477,40 +507,43 @@ size_t dwt_workspace_bytes(int64_t N, int64_t C, int64_t HW, int group_size, int
 
 int dwt_whiten_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, int group_size, int n_domains,
                    int mode, float eps, float momentum, int update_running, float* const* running_mean,
-                   float* const* running_cov, const float* gamma, const float* beta, const float* residual, int epilogue,
-                   float* save_mean, float* save_w, void* workspace, size_t workspace_bytes, dwt_stream_t stream) {
+                   float* const* running_cov, const float* gamma, const float* beta, const float* residual,
+                   uint8_t* relu_mask, int epilogue, float* save_mean, float* save_w, void* workspace,
+                   size_t workspace_bytes, dwt_stream_t stream) {
   return whiten_like_fwd(x, y, N, C, HW, group_size, n_domains, mode, 1.f - eps, eps, momentum, 1.f, update_running,
-                         running_mean, running_cov, gamma, beta, residual, epilogue, save_mean, save_w, workspace,
-                         workspace_bytes, (cudaStream_t)stream);
+                         running_mean, running_cov, gamma, beta, residual, relu_mask, epilogue, save_mean, save_w,
+                         workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int dwt_whiten_bwd(const float* x, const float* dout, float* dx, int64_t N, int64_t C, int64_t HW, int group_size,
                    int n_domains, int mode, float eps, const float* save_mean, const float* save_w,
-                   const float* gamma, const float* beta, int epilogue, float* dgamma, float* dbeta, void* workspace,
-                   size_t workspace_bytes, dwt_stream_t stream) {
+                   const float* gamma, const float* beta, const uint8_t* relu_mask, float* dresidual, int epilogue,
+                   float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, dwt_stream_t stream) {
   return whiten_like_bwd(x, dout, dx, N, C, HW, group_size, n_domains, mode, 1.f - eps, save_mean, save_w, gamma,
-                         beta, epilogue, dgamma, dbeta, workspace, workspace_bytes, (cudaStream_t)stream);
+                         beta, relu_mask, dresidual, epilogue, dgamma, dbeta, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
 }
 
 // Batch norm is the group-size-1 member of the same family: "covariance" = biased variance,
 // S = var + eps, W = 1/sqrt(S) = invstd; only the EMA differs (unbiased variance).
 int dwt_bn_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, int n_domains, int mode, float eps,
                float factor, int update_running, float* const* running_mean, float* const* running_var,
-               const float* weight, const float* bias, const float* residual, int epilogue, float* save_mean,
-               float* save_invstd, void* workspace, size_t workspace_bytes, dwt_stream_t stream) {
+               const float* weight, const float* bias, const float* residual, uint8_t* relu_mask, int epilogue,
+               float* save_mean, float* save_invstd, void* workspace, size_t workspace_bytes, dwt_stream_t stream) {
   const double M = (double)N * (double)HW;
   const float unbias = M > 1.0 ? (float)(M / (M - 1.0)) : 1.f;
   return whiten_like_fwd(x, y, N, C, HW, 1, n_domains, mode, 1.f, eps, factor, unbias, update_running, running_mean,
-                         running_var, weight, bias, residual, epilogue, save_mean, save_invstd, workspace, workspace_bytes,
-                         (cudaStream_t)stream);
+                         running_var, weight, bias, residual, relu_mask, epilogue, save_mean, save_invstd, workspace,
+                         workspace_bytes, (cudaStream_t)stream);
 }
 
 int dwt_bn_bwd(const float* x, const float* dout, float* dx, int64_t N, int64_t C, int64_t HW, int n_domains,
                int mode, const float* save_mean, const float* save_invstd, const float* weight, const float* bias,
-               int epilogue, float* dweight, float* dbias, void* workspace, size_t workspace_bytes,
-               dwt_stream_t stream) {
+               const uint8_t* relu_mask, float* dresidual, int epilogue, float* dweight, float* dbias, void* workspace,
+               size_t workspace_bytes, dwt_stream_t stream) {
   return whiten_like_bwd(x, dout, dx, N, C, HW, 1, n_domains, mode, 1.f, save_mean, save_invstd, weight, bias,
-                         epilogue, dweight, dbias, workspace, workspace_bytes, (cudaStream_t)stream);
+                         relu_mask, dresidual, epilogue, dweight, dbias, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
 }
 
 int dwt_mec_fwd_bwd(const float* x, const float* y, int64_t N, int64_t K, float* loss, float* gx, float* gy,
@@ -525,12 +558,13 @@ int dwt_mec_fwd_bwd(const float* x, const float* y, int64_t N, int64_t K, float*
 }
 
 int dwt_head_loss_fwd_bwd(const float* logits, const int64_t* labels, int64_t B, int64_t K, float lambda, float* losses,
-                          float* grad, dwt_stream_t stream) {
+                          float* grad, int* status, dwt_stream_t stream) {
   if (!logits || !labels || !losses || !grad) return fail(DWT_E_INVALID, "null pointer argument");
   if (B <= 0 || K <= 0 || B >= (1 << 22) || K >= (1 << 24)) return fail(DWT_E_INVALID, "bad logits shape [3*%lld,%lld]", (long long)B, (long long)K);
   {
     Launch l("head_loss", nullptr, 4.0 * 3 * (double)B * (double)K * 2, (cudaStream_t)stream);
-    dwt::head_loss_launch(logits, reinterpret_cast<const long long*>(labels), (int)B, (int)K, lambda, losses, grad, (cudaStream_t)stream);
+    dwt::head_loss_launch(logits, reinterpret_cast<const long long*>(labels), (int)B, (int)K, lambda, losses, grad, status,
+                          (cudaStream_t)stream);
   }
   return check_launch("head loss kernel");
 }

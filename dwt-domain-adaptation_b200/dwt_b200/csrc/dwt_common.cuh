@@ -46,6 +46,9 @@ struct FwdFin {
   float* rcov[DWT_MAX_DOMAINS];
   int* dom_counter;      // [G]
   int* status;
+  int* bad;              // [D][G] scratch: 1 when the batch covariance of (d, g) was not positive definite -- the
+                         // reference raises from torch.cholesky before its EMA lines (whitening.py:53 vs :57-59), so
+                         // that domain's update of the (possibly shared) running buffers is skipped
 };
 
 struct BwdFin {
@@ -135,10 +138,11 @@ __device__ inline void fwd_factor_block(const Geom& gm, const FwdFin& f, int d, 
   }
   __syncthreads();
   // right-looking Cholesky, lower triangle of sL in place
+  bool bad = false;                                 // meaningful in thread 0
   for (int k = 0; k < GS; ++k) {
     if (tid == 0) {
       float piv = sL[k * LD + k];
-      if (!(piv > 0.f)) atomicOr(f.status, 1);
+      bad |= !(piv > 0.f);
       sL[k * LD + k] = sqrtf(piv);
     }
     __syncthreads();
@@ -166,6 +170,10 @@ __device__ inline void fwd_factor_block(const Geom& gm, const FwdFin& f, int d, 
     int i = e / GS, j = e - i * GS;
     f.save_w[gbase + e] = sW[i * LD + j];
   }
+  if (tid == 0) {
+    if (bad) atomicOr(f.status, DWT_STATUS_NOT_PD);
+    if (store_cov) f.bad[d * gm.G + g] = bad ? 1 : 0;
+  }
 }
 
 // EMA of the running buffers, domain by domain in order so that aliased buffers end as
@@ -177,6 +185,7 @@ __device__ inline void fwd_ema_block(const Geom& gm, const FwdFin& f, int g, int
   const float m = f.momentum, k = 1.f - f.momentum;
   for (int e = tid; e < GS * GS + GS; e += nt) {
     for (int d = 0; d < gm.D; ++d) {
+      if (__ldcg(f.bad + d * gm.G + g)) continue;
       if (e < GS * GS) {
         float c = __ldcg(f.save_cov + ((size_t)d * gm.G + g) * GS * GS + e) * f.unbias;
         float* p = f.rcov[d] + (size_t)g * GS * GS + e;

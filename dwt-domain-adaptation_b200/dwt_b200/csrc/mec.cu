@@ -71,16 +71,37 @@ __global__ void __launch_bounds__(kMecThreads) mec_kernel(const float* __restric
 //   logits [3B, K] = source | target | target-aug ;  labels [B]
 //   loss = mean_n NLL(log_softmax(source_n), label_n) + lambda * MEC(target, target-aug)
 // losses[0..2] = total, classification, lambda*MEC ; grad [3B, K] = d total / d logits.
+// Labels follow F.nll_loss (the reference's call, defaults): label -100 (ignore_index) drops the row from the
+// sum AND from the mean's denominator; any other label outside [0, K) is an error there (device assert) --
+// here it is never dereferenced: the row is dropped like an ignored one and bit 1 of *status is set.
 __global__ void __launch_bounds__(kMecThreads) head_loss_kernel(const float* __restrict__ logits,
                                                                  const long long* __restrict__ labels, int B, int K,
                                                                  float lambda, float* __restrict__ losses,
-                                                                 float* __restrict__ grad) {
+                                                                 float* __restrict__ grad, int* __restrict__ status) {
   __shared__ float sCls[kMecThreads / 32], sMec[kMecThreads / 32];
+  __shared__ int sValid;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) sValid = 0;
+  __syncthreads();
+  {
+    int nv = 0, bad = 0;
+    for (int n = threadIdx.x; n < B; n += blockDim.x) {
+      const long long y = labels[n];
+      if (y >= 0 && y < K) ++nv;
+      else if (y != -100) bad = 1;
+    }
+    if (nv) atomicAdd(&sValid, nv);
+    if (bad && status != nullptr) atomicOr(status, DWT_STATUS_BAD_LABEL);
+  }
+  __syncthreads();
+  const int valid = sValid;
   float cls = 0.f, mec = 0.f;
   for (int n = warp; n < 2 * B; n += nwarps) {
     if (n < B) {                                   // source row: softmax cross-entropy
       const float* xr = logits + (size_t)n * K;
+      const long long yl = labels[n];
+      const bool use = yl >= 0 && yl < K;
+      const int y = use ? (int)yl : 0;
       float mx = -FLT_MAX;
       for (int k = lane; k < K; k += 32) mx = fmaxf(mx, xr[k]);
       mx = warp_max(mx);
@@ -88,9 +109,8 @@ __global__ void __launch_bounds__(kMecThreads) head_loss_kernel(const float* __r
       for (int k = lane; k < K; k += 32) sx += expf(xr[k] - mx);
       sx = warp_sum(sx);
       const float lz = mx + logf(sx);
-      const int y = (int)labels[n];
-      cls += (lane == 0) ? (lz - xr[y]) : 0.f;
-      const float sc = 1.f / (float)B;
+      cls += (lane == 0 && use) ? (lz - xr[y]) : 0.f;
+      const float sc = use ? 1.f / (float)valid : 0.f;
       for (int k = lane; k < K; k += 32) grad[(size_t)n * K + k] = sc * (expf(xr[k] - lz) - (k == y ? 1.f : 0.f));
     } else {                                       // target row n and its augmented twin n + B: MEC
       const float* xr = logits + (size_t)n * K;
@@ -127,7 +147,8 @@ __global__ void __launch_bounds__(kMecThreads) head_loss_kernel(const float* __r
   if (threadIdx.x == 0) {
     float c = 0.f, m = 0.f;
     for (int w = 0; w < nwarps; ++w) { c += sCls[w]; m += sMec[w]; }
-    c /= (float)B; m = lambda * m / (float)B;
+    c /= (float)valid;                              // 0/0 = NaN when every label is ignored, like F.nll_loss
+    m = lambda * m / (float)B;
     losses[0] = c + m; losses[1] = c; losses[2] = m;
   }
 }
@@ -135,11 +156,11 @@ __global__ void __launch_bounds__(kMecThreads) head_loss_kernel(const float* __r
 }  // namespace
 
 void head_loss_launch(const float* logits, const long long* labels, int B, int K, float lambda, float* losses,
-                      float* grad, cudaStream_t st) {
+                      float* grad, int* status, cudaStream_t st) {
   int threads = 2 * B * 32;
   if (threads > kMecThreads) threads = kMecThreads;
   if (threads < 32) threads = 32;
-  head_loss_kernel<<<1, threads, 0, st>>>(logits, labels, B, K, lambda, losses, grad);
+  head_loss_kernel<<<1, threads, 0, st>>>(logits, labels, B, K, lambda, losses, grad, status);
 }
 
 void mec_launch(const float* x, const float* y, int N, int K, float* loss, float* gx, float* gy, cudaStream_t st) {

@@ -17,6 +17,20 @@
 //   cl_stats -> vec_reduce -> cl_fwd_finalize -> cl_apply          (forward, 12 B/element)
 //   cl_bwd_reduce -> vec_reduce -> cl_bwd_finalize -> cl_bwd_apply (backward, 20 B/element)
 //
+// Sweep order (round 2).  The tensor a pass reads was touched a moment ago: x was just WRITTEN front to back
+// by the producing convolution, and the second pass of a site re-reads what the first pass just read.  126 MB
+// of it are still in L2 -- but only if the kernel gets to them before its own misses evict them (inside the
+// bench step cl_stats ran at 0.81 of the HBM peak although the same launch alone under ncu reads at 0.99: the
+// difference is the write-back of the producer's dirty lines).  So every kernel is a persistent grid of CTAs
+// that together sweep the tensor as ONE moving window of consecutive 32-row chunks (chunk c -> CTA c mod grid):
+// the two reductions sweep from the END of the tensor to its start (newest bytes first, domains D-1..0 one
+// after the other), the two elementwise passes from the START to the end (where the reduction just finished).
+// A CTA's partial sums are still a fixed set added in a fixed order: results stay deterministic.
+//
+// The residual tail relu(z + identity) (resnet50_dwt_mec_officehome.py:239-240): the forward apply leaves one
+// byte per float4 with the four (out > 0) bits; the backward passes mask dout with it (the pre-activation cannot
+// be recomputed without the residual) and bwd_apply also writes the masked gradient for the identity branch.
+//
 // Reference semantics: utils/whitening.py:37-61, utils/batch_norm.py:54-69 (/root/reference).
 #include "dwt_common.cuh"
 #include "norm_launch.h"
@@ -39,7 +53,6 @@ template <int GS> struct ClShape {
 // Thread placement inside the CTA.
 struct ClThread {
   int C4, CW, rpi, col, rsub, q;
-  unsigned r0, r1;            // row range of this CTA inside the domain
   __device__ __forceinline__ ClThread(const Geom& gm) {
     C4 = gm.C >> 2;
     CW = C4 < kT ? C4 : kT;
@@ -47,11 +60,20 @@ struct ClThread {
     col = threadIdx.x % CW;
     rsub = threadIdx.x / CW;
     q = blockIdx.y * CW + col;
-    const unsigned rows = (unsigned)gm.N * gm.HW;
-    r0 = (unsigned)((unsigned long long)rows * blockIdx.x / gridDim.x);
-    r1 = (unsigned)((unsigned long long)rows * (blockIdx.x + 1) / gridDim.x);
   }
 };
+
+// The CTAs of grid.x sweep the rows of one domain as a moving window of chunks of rpi*UNROLL consecutive rows:
+// chunk c belongs to CTA c mod gridDim.x; DESC walks from the last chunk to the first.  body(r) gets the first
+// row of the calling thread inside the chunk (its rows are r + u*rpi, u < UNROLL, to be guarded by r < rows).
+template <int UNROLL, bool DESC, class F>
+__device__ __forceinline__ void sweep_rows(const ClThread& t, unsigned rows, F&& body) {
+  const unsigned krows = (unsigned)t.rpi * UNROLL, nch = (rows + krows - 1) / krows;
+  for (unsigned i = blockIdx.x; i < nch; i += gridDim.x) body((DESC ? nch - 1 - i : i) * krows + t.rsub);
+}
+// Domains served by this CTA: all of them one after the other (gridDim.z == 1) or one (gridDim.z == D).
+#define CL_FOR_DOMAINS(d, gm, DESC) \
+  for (int di_ = blockIdx.z, d = (DESC) ? (gm).D - 1 - di_ : di_; di_ < (gm).D; di_ += gridDim.z, d = (DESC) ? (gm).D - 1 - di_ : di_)
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -83,51 +105,53 @@ __global__ void __launch_bounds__(kT, 3) cl_stats_kernel(const float* __restrict
   constexpr int UNROLL = 8;
   __shared__ float sRed[kT * S::FWD];
   const ClThread t(gm);
-  const int d = blockIdx.z;
   const unsigned rows = (unsigned)gm.N * gm.HW;
-  const float* xd = x + (size_t)d * rows * gm.C + 4 * t.q;
-  // pilot shift: mean of the first <= 8 rows of the domain, per channel (every thread of a column agrees)
-  float K[4] = {0.f, 0.f, 0.f, 0.f};
-  {
-    const unsigned np = rows < 8 ? rows : 8;
-    for (unsigned r = 0; r < np; ++r) {
-      const float4 v = ldg4(xd + (size_t)r * gm.C);
-      K[0] += v.x; K[1] += v.y; K[2] += v.z; K[3] += v.w;
+  CL_FOR_DOMAINS(d, gm, true) {
+    const float* xd = x + (size_t)d * rows * gm.C + 4 * t.q;
+    // pilot shift: mean of the first <= 8 rows of the domain, per channel (every thread of a column agrees)
+    float K[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const unsigned np = rows < 8 ? rows : 8;
+      for (unsigned r = 0; r < np; ++r) {
+        const float4 v = ldg4(xd + (size_t)r * gm.C);
+        K[0] += v.x; K[1] += v.y; K[2] += v.z; K[3] += v.w;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) K[c] /= (float)np;
+      if (blockIdx.x == 0 && t.rsub == 0) *reinterpret_cast<float4*>(shift + (size_t)d * gm.C + 4 * t.q) = make_float4(K[0], K[1], K[2], K[3]);
     }
+    float acc[S::FWD];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) K[c] /= (float)np;
-    if (blockIdx.x == 0 && t.rsub == 0) *reinterpret_cast<float4*>(shift + (size_t)d * gm.C + 4 * t.q) = make_float4(K[0], K[1], K[2], K[3]);
-  }
-  float acc[S::FWD];
+    for (int i = 0; i < S::FWD; ++i) acc[i] = 0.f;
+    sweep_rows<UNROLL, true>(t, rows, [&](unsigned r) {
+      float4 v[UNROLL];
 #pragma unroll
-  for (int i = 0; i < S::FWD; ++i) acc[i] = 0.f;
-  for (unsigned r = t.r0 + t.rsub; r < t.r1; r += t.rpi * UNROLL) {
-    float4 v[UNROLL];
+      for (int u = 0; u < UNROLL; ++u) {
+        const unsigned rr = r + u * t.rpi;
+        v[u] = rr < rows ? ldg4(xd + (size_t)rr * gm.C) : make_float4(K[0], K[1], K[2], K[3]);
+      }
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const unsigned rr = r + u * t.rpi;
-      v[u] = rr < t.r1 ? ldg4(xd + (size_t)rr * gm.C) : make_float4(K[0], K[1], K[2], K[3]);
-    }
+      for (int u = 0; u < UNROLL; ++u) {
+        const float e[4] = {v[u].x - K[0], v[u].y - K[1], v[u].z - K[2], v[u].w - K[3]};
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const float e[4] = {v[u].x - K[0], v[u].y - K[1], v[u].z - K[2], v[u].w - K[3]};
+        for (int s = 0; s < S::NSUB; ++s) {
 #pragma unroll
-      for (int s = 0; s < S::NSUB; ++s) {
+          for (int c = 0; c < GS; ++c) {
+            acc[s * S::FWD1 + c] += e[s * GS + c];
 #pragma unroll
-        for (int c = 0; c < GS; ++c) {
-          acc[s * S::FWD1 + c] += e[s * GS + c];
-#pragma unroll
-          for (int j = 0; j <= c; ++j)
-            acc[s * S::FWD1 + GS + c * (c + 1) / 2 + j] = fmaf(e[s * GS + c], e[s * GS + j], acc[s * S::FWD1 + GS + c * (c + 1) / 2 + j]);
+            for (int j = 0; j <= c; ++j)
+              acc[s * S::FWD1 + GS + c * (c + 1) / 2 + j] = fmaf(e[s * GS + c], e[s * GS + j], acc[s * S::FWD1 + GS + c * (c + 1) / 2 + j]);
+          }
         }
       }
-    }
-  }
-  column_reduce<S::FWD>(t, acc, sRed);
-  if (t.rsub == 0) {
-    float* dst = partial + (((size_t)d * gridDim.x + blockIdx.x) * t.C4 + t.q) * S::FWD;
+    });
+    column_reduce<S::FWD>(t, acc, sRed);
+    if (t.rsub == 0) {
+      float* dst = partial + (((size_t)d * gridDim.x + blockIdx.x) * t.C4 + t.q) * S::FWD;
 #pragma unroll
-    for (int i = 0; i < S::FWD; ++i) dst[i] = acc[i];
+      for (int i = 0; i < S::FWD; ++i) dst[i] = acc[i];
+    }
+    if (gridDim.z == 1) __syncthreads();             // sRed is reused by the next domain
   }
 }
 
@@ -172,6 +196,7 @@ __global__ void __launch_bounds__(256) cl_fwd_finalize_kernel(const float* __res
   using SH = ClShape<GS>;
   constexpr int NST = GS + GS * GS;
   __shared__ float sStat[DWT_MAX_DOMAINS][64][NST + 1];
+  __shared__ unsigned char sBad[DWT_MAX_DOMAINS][64];
   const int gl = threadIdx.x, d = threadIdx.y, g = blockIdx.x * 64 + gl;
   const int W = (gm.C >> 2) * SH::FWD;
   const float invM = 1.f / gm.M;
@@ -193,7 +218,7 @@ __global__ void __launch_bounds__(256) cl_fwd_finalize_kernel(const float* __res
         const float c = a[GS + i * (i + 1) / 2 + j] * invM - (a[i] * invM) * (a[j] * invM);
         cov[i][j] = c; cov[j][i] = c;
       }
-    factor_thread<GS>(gm, fin, d, g, mean, cov, false);
+    sBad[d][gl] = factor_thread<GS>(gm, fin, d, g, mean, cov, false) ? 1 : 0;
 #pragma unroll
     for (int i = 0; i < GS; ++i) {
       sStat[d][gl][i] = mean[i];
@@ -203,7 +228,8 @@ __global__ void __launch_bounds__(256) cl_fwd_finalize_kernel(const float* __res
   }
   __syncthreads();
   if (fin.update_running && d == 0 && g < gm.G)
-    for (int dd = 0; dd < gm.D; ++dd) ema_direct<GS>(gm, fin, dd, g, &sStat[dd][gl][0], &sStat[dd][gl][GS]);
+    for (int dd = 0; dd < gm.D; ++dd)
+      if (!sBad[dd][gl]) ema_direct<GS>(gm, fin, dd, g, &sStat[dd][gl][0], &sStat[dd][gl][GS]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -213,55 +239,61 @@ template <int GS, int EPI>
 __global__ void __launch_bounds__(kT, 3) cl_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const Geom gm,
                                                          const float* __restrict__ save_mean, const float* __restrict__ save_w,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         const float* __restrict__ res) {
+                                                         const float* __restrict__ res, uint8_t* __restrict__ mask) {
   using S = ClShape<GS>;
   constexpr bool RES = (EPI & DWT_EPI_RESIDUAL) != 0;
   constexpr int UNROLL = RES ? 4 : 8;
   const ClThread t(gm);
-  const int d = blockIdx.z;
-  float Wp[S::NSUB][S::NM], bp[S::NSUB][GS];
+  const unsigned rows = (unsigned)gm.N * gm.HW;
+  CL_FOR_DOMAINS(d, gm, false) {
+    float Wp[S::NSUB][S::NM], bp[S::NSUB][GS];
 #pragma unroll
-  for (int s = 0; s < S::NSUB; ++s) {
-    const int g = t.q * S::NSUB + s;
-    load_forward_map<GS, EPI>(save_w + ((size_t)d * gm.G + g) * GS * GS, save_mean + (size_t)d * gm.C + g * GS,
-                              gamma + g * GS, beta + g * GS, Wp[s], bp[s]);
-  }
-  const size_t base = (size_t)d * gm.N * gm.HW * gm.C + 4 * t.q;
-  const float* xd = x + base;
-  const float* rd = res + base;
-  float* yd = y + base;
-  for (unsigned r = t.r0 + t.rsub; r < t.r1; r += t.rpi * UNROLL) {
-    float4 v[UNROLL], rs[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const unsigned rr = r + u * t.rpi;
-      if (rr < t.r1) {
-        v[u] = ldg4(xd + (size_t)rr * gm.C);
-        if constexpr (RES) rs[u] = ldg4(rd + (size_t)rr * gm.C);
-      }
+    for (int s = 0; s < S::NSUB; ++s) {
+      const int g = t.q * S::NSUB + s;
+      load_forward_map<GS, EPI>(save_w + ((size_t)d * gm.G + g) * GS * GS, save_mean + (size_t)d * gm.C + g * GS,
+                                gamma + g * GS, beta + g * GS, Wp[s], bp[s]);
     }
+    const size_t base = (size_t)d * rows * gm.C + 4 * t.q;
+    const float* xd = x + base;
+    const float* rd = res + base;
+    float* yd = y + base;
+    uint8_t* md = mask + (size_t)d * rows * t.C4 + t.q;          // one byte per float4: the four (out > 0) bits
+    sweep_rows<UNROLL, false>(t, rows, [&](unsigned r) {
+      float4 v[UNROLL], rs[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const unsigned rr = r + u * t.rpi;
-      if (rr < t.r1) {
-        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-        float o[4], ra[4] = {0.f, 0.f, 0.f, 0.f};
-        if constexpr (RES) { ra[0] = rs[u].x; ra[1] = rs[u].y; ra[2] = rs[u].z; ra[3] = rs[u].w; }
-#pragma unroll
-        for (int s = 0; s < S::NSUB; ++s) {
-          float xi[GS], oi[GS];
-#pragma unroll
-          for (int c = 0; c < GS; ++c) xi[c] = e[s * GS + c];
-          apply_group<GS>(Wp[s], bp[s], xi, oi);
-#pragma unroll
-          for (int c = 0; c < GS; ++c) {
-            const float z = RES ? oi[c] + ra[s * GS + c] : oi[c];
-            o[s * GS + c] = (EPI & DWT_EPI_RELU) ? fmaxf(z, 0.f) : z;
-          }
+      for (int u = 0; u < UNROLL; ++u) {
+        const unsigned rr = r + u * t.rpi;
+        if (rr < rows) {
+          v[u] = ldg4(xd + (size_t)rr * gm.C);
+          if constexpr (RES) rs[u] = ldg4(rd + (size_t)rr * gm.C);
         }
-        *reinterpret_cast<float4*>(yd + (size_t)rr * gm.C) = make_float4(o[0], o[1], o[2], o[3]);
       }
-    }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const unsigned rr = r + u * t.rpi;
+        if (rr < rows) {
+          const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          float o[4], ra[4] = {0.f, 0.f, 0.f, 0.f};
+          if constexpr (RES) { ra[0] = rs[u].x; ra[1] = rs[u].y; ra[2] = rs[u].z; ra[3] = rs[u].w; }
+          unsigned bits = 0;
+#pragma unroll
+          for (int s = 0; s < S::NSUB; ++s) {
+            float xi[GS], oi[GS];
+#pragma unroll
+            for (int c = 0; c < GS; ++c) xi[c] = e[s * GS + c];
+            apply_group<GS>(Wp[s], bp[s], xi, oi);
+#pragma unroll
+            for (int c = 0; c < GS; ++c) {
+              const float z = RES ? oi[c] + ra[s * GS + c] : oi[c];
+              if constexpr (RES) bits |= (z > 0.f ? 1u : 0u) << (s * GS + c);
+              o[s * GS + c] = (EPI & DWT_EPI_RELU) ? fmaxf(z, 0.f) : z;
+            }
+          }
+          *reinterpret_cast<float4*>(yd + (size_t)rr * gm.C) = make_float4(o[0], o[1], o[2], o[3]);
+          if constexpr (RES) { if (mask != nullptr) md[(size_t)rr * t.C4] = (uint8_t)bits; }
+        }
+      }
+    });
   }
 }
 
@@ -272,67 +304,83 @@ template <int GS, int EPI>
 __global__ void __launch_bounds__(kT, 2) cl_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dout,
                                                               const Geom gm, const float* __restrict__ save_mean,
                                                               const float* __restrict__ save_w, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, float* __restrict__ partial) {
+                                                              const float* __restrict__ beta, const uint8_t* __restrict__ mask,
+                                                              float* __restrict__ partial) {
   using S = ClShape<GS>;
   constexpr int UNROLL = 4;
-  constexpr bool RELU = (EPI & DWT_EPI_RELU) != 0;
+  constexpr bool MASK = (EPI & DWT_EPI_RESIDUAL) != 0;          // ReLU mask saved by the forward (residual tail)
+  constexpr bool RELU = (EPI & DWT_EPI_RELU) != 0 && !MASK;     // ReLU mask recomputed from x
   __shared__ float sRed[kT * S::BWD];
   const ClThread t(gm);
-  const int d = blockIdx.z;
-  float Wp[S::NSUB][S::NM], bp[S::NSUB][GS], mu[4];
+  const unsigned rows = (unsigned)gm.N * gm.HW;
+  CL_FOR_DOMAINS(d, gm, true) {
+    float Wp[S::NSUB][S::NM], bp[S::NSUB][GS], mu[4];
 #pragma unroll
-  for (int s = 0; s < S::NSUB; ++s) {
-    const int g = t.q * S::NSUB + s;
-    if constexpr (RELU)
-      load_forward_map<GS, EPI>(save_w + ((size_t)d * gm.G + g) * GS * GS, save_mean + (size_t)d * gm.C + g * GS,
-                                gamma + g * GS, beta + g * GS, Wp[s], bp[s]);
-  }
-  {
-    const float4 m4 = ldg4(save_mean + (size_t)d * gm.C + 4 * t.q);
-    mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w;
-  }
-  float acc[S::BWD];
-#pragma unroll
-  for (int i = 0; i < S::BWD; ++i) acc[i] = 0.f;
-  const size_t base = (size_t)d * gm.N * gm.HW * gm.C + 4 * t.q;
-  const float* xd = x + base;
-  const float* gd = dout + base;
-  for (unsigned r = t.r0 + t.rsub; r < t.r1; r += t.rpi * UNROLL) {
-    float4 v[UNROLL], q[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const unsigned rr = r + u * t.rpi;
-      if (rr < t.r1) { v[u] = ldg4(xd + (size_t)rr * gm.C); q[u] = ldg4(gd + (size_t)rr * gm.C); }
-      else { v[u] = make_float4(mu[0], mu[1], mu[2], mu[3]); q[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    for (int s = 0; s < S::NSUB; ++s) {
+      const int g = t.q * S::NSUB + s;
+      if constexpr (RELU)
+        load_forward_map<GS, EPI>(save_w + ((size_t)d * gm.G + g) * GS * GS, save_mean + (size_t)d * gm.C + g * GS,
+                                  gamma + g * GS, beta + g * GS, Wp[s], bp[s]);
     }
+    {
+      const float4 m4 = ldg4(save_mean + (size_t)d * gm.C + 4 * t.q);
+      mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w;
+    }
+    float acc[S::BWD];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, ge[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+    for (int i = 0; i < S::BWD; ++i) acc[i] = 0.f;
+    const size_t base = (size_t)d * rows * gm.C + 4 * t.q;
+    const float* xd = x + base;
+    const float* gd = dout + base;
+    const uint8_t* md = mask + (size_t)d * rows * t.C4 + t.q;
+    sweep_rows<UNROLL, true>(t, rows, [&](unsigned r) {
+      float4 v[UNROLL], q[UNROLL];
+      unsigned mb[UNROLL];
 #pragma unroll
-      for (int s = 0; s < S::NSUB; ++s) {
-        float xi[GS], dz[GS];
-#pragma unroll
-        for (int c = 0; c < GS; ++c) { xi[c] = e[s * GS + c]; dz[c] = ge[s * GS + c]; }
-        if constexpr (RELU) {
-          float oi[GS];
-          apply_group<GS>(Wp[s], bp[s], xi, oi);
-#pragma unroll
-          for (int c = 0; c < GS; ++c) dz[c] = oi[c] > 0.f ? dz[c] : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < GS; ++i) {
-          acc[s * S::BWD1 + GS * GS + i] += dz[i];
-#pragma unroll
-          for (int j = 0; j < GS; ++j) acc[s * S::BWD1 + i * GS + j] = fmaf(dz[i], xi[j] - mu[s * GS + j], acc[s * S::BWD1 + i * GS + j]);
+      for (int u = 0; u < UNROLL; ++u) {
+        const unsigned rr = r + u * t.rpi;
+        if (rr < rows) {
+          v[u] = ldg4(xd + (size_t)rr * gm.C); q[u] = ldg4(gd + (size_t)rr * gm.C);
+          if constexpr (MASK) mb[u] = __ldg(md + (size_t)rr * t.C4);
+        } else {
+          v[u] = make_float4(mu[0], mu[1], mu[2], mu[3]); q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (MASK) mb[u] = 0u;
         }
       }
-    }
-  }
-  column_reduce<S::BWD>(t, acc, sRed);
-  if (t.rsub == 0) {
-    float* dst = partial + (((size_t)d * gridDim.x + blockIdx.x) * t.C4 + t.q) * S::BWD;
 #pragma unroll
-    for (int i = 0; i < S::BWD; ++i) dst[i] = acc[i];
+      for (int u = 0; u < UNROLL; ++u) {
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, ge[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int s = 0; s < S::NSUB; ++s) {
+          float xi[GS], dz[GS];
+#pragma unroll
+          for (int c = 0; c < GS; ++c) { xi[c] = e[s * GS + c]; dz[c] = ge[s * GS + c]; }
+          if constexpr (RELU) {
+            float oi[GS];
+            apply_group<GS>(Wp[s], bp[s], xi, oi);
+#pragma unroll
+            for (int c = 0; c < GS; ++c) dz[c] = oi[c] > 0.f ? dz[c] : 0.f;
+          }
+          if constexpr (MASK) {
+#pragma unroll
+            for (int c = 0; c < GS; ++c) dz[c] = ((mb[u] >> (s * GS + c)) & 1u) ? dz[c] : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < GS; ++i) {
+            acc[s * S::BWD1 + GS * GS + i] += dz[i];
+#pragma unroll
+            for (int j = 0; j < GS; ++j) acc[s * S::BWD1 + i * GS + j] = fmaf(dz[i], xi[j] - mu[s * GS + j], acc[s * S::BWD1 + i * GS + j]);
+          }
+        }
+      }
+    });
+    column_reduce<S::BWD>(t, acc, sRed);
+    if (t.rsub == 0) {
+      float* dst = partial + (((size_t)d * gridDim.x + blockIdx.x) * t.C4 + t.q) * S::BWD;
+#pragma unroll
+      for (int i = 0; i < S::BWD; ++i) dst[i] = acc[i];
+    }
+    if (gridDim.z == 1) __syncthreads();             // sRed is reused by the next domain
   }
 }
 
@@ -376,74 +424,90 @@ template <int GS, int EPI>
 __global__ void __launch_bounds__(kT, 2) cl_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dout,
                                                              float* __restrict__ dx, const Geom gm, const float* __restrict__ coef,
                                                              const float* __restrict__ save_mean, const float* __restrict__ save_w,
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta) {
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const uint8_t* __restrict__ mask, float* __restrict__ dres) {
   using S = ClShape<GS>;
   constexpr int UNROLL = 4;
-  constexpr bool RELU = (EPI & DWT_EPI_RELU) != 0;
+  constexpr bool MASK = (EPI & DWT_EPI_RESIDUAL) != 0;
+  constexpr bool RELU = (EPI & DWT_EPI_RELU) != 0 && !MASK;
   const ClThread t(gm);
-  const int d = blockIdx.z;
-  float Wp[S::NSUB][S::NM], bp[S::NSUB][GS], A1[S::NSUB][S::NM], Bm[S::NSUB][S::NM], cv[S::NSUB][GS];
+  const unsigned rows = (unsigned)gm.N * gm.HW;
+  CL_FOR_DOMAINS(d, gm, false) {
+    float Wp[S::NSUB][S::NM], bp[S::NSUB][GS], A1[S::NSUB][S::NM], Bm[S::NSUB][S::NM], cv[S::NSUB][GS];
 #pragma unroll
-  for (int s = 0; s < S::NSUB; ++s) {
-    const int g = t.q * S::NSUB + s;
-    if constexpr (RELU)
-      load_forward_map<GS, EPI>(save_w + ((size_t)d * gm.G + g) * GS * GS, save_mean + (size_t)d * gm.C + g * GS,
-                                gamma + g * GS, beta + g * GS, Wp[s], bp[s]);
-    const float* cf = coef + ((size_t)d * gm.G + g) * coef_stride(GS);
+    for (int s = 0; s < S::NSUB; ++s) {
+      const int g = t.q * S::NSUB + s;
+      if constexpr (RELU)
+        load_forward_map<GS, EPI>(save_w + ((size_t)d * gm.G + g) * GS * GS, save_mean + (size_t)d * gm.C + g * GS,
+                                  gamma + g * GS, beta + g * GS, Wp[s], bp[s]);
+      const float* cf = coef + ((size_t)d * gm.G + g) * coef_stride(GS);
 #pragma unroll
-    for (int i = 0; i < GS; ++i) {
-      cv[s][i] = __ldg(cf + 2 * GS * GS + i);
+      for (int i = 0; i < GS; ++i) {
+        cv[s][i] = __ldg(cf + 2 * GS * GS + i);
 #pragma unroll
-      for (int j = 0; j <= i; ++j) {
-        A1[s][i * (i + 1) / 2 + j] = __ldg(cf + j * GS + i);
-        Bm[s][i * (i + 1) / 2 + j] = __ldg(cf + GS * GS + i * GS + j);
-      }
-    }
-  }
-  const size_t base = (size_t)d * gm.N * gm.HW * gm.C + 4 * t.q;
-  const float* xd = x + base;
-  const float* gd = dout + base;
-  float* od = dx + base;
-  for (unsigned r = t.r0 + t.rsub; r < t.r1; r += t.rpi * UNROLL) {
-    float4 v[UNROLL], q[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const unsigned rr = r + u * t.rpi;
-      if (rr < t.r1) { v[u] = ldg4(xd + (size_t)rr * gm.C); q[u] = ldg4(gd + (size_t)rr * gm.C); }
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const unsigned rr = r + u * t.rpi;
-      if (rr < t.r1) {
-        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, ge[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-        float o[4];
-#pragma unroll
-        for (int s = 0; s < S::NSUB; ++s) {
-          float xi[GS], dz[GS];
-#pragma unroll
-          for (int c = 0; c < GS; ++c) { xi[c] = e[s * GS + c]; dz[c] = ge[s * GS + c]; }
-          if constexpr (RELU) {
-            float oi[GS];
-            apply_group<GS>(Wp[s], bp[s], xi, oi);
-#pragma unroll
-            for (int c = 0; c < GS; ++c) dz[c] = oi[c] > 0.f ? dz[c] : 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < GS; ++i) {
-            float a = cv[s][i];
-#pragma unroll
-            for (int j = i; j < GS; ++j) a = fmaf(A1[s][j * (j + 1) / 2 + i], dz[j], a);
-#pragma unroll
-            for (int j = 0; j < GS; ++j) {
-              const int hi = i > j ? i : j, lo = i > j ? j : i;
-              a = fmaf(Bm[s][hi * (hi + 1) / 2 + lo], xi[j], a);
-            }
-            o[s * GS + i] = a;
-          }
+        for (int j = 0; j <= i; ++j) {
+          A1[s][i * (i + 1) / 2 + j] = __ldg(cf + j * GS + i);
+          Bm[s][i * (i + 1) / 2 + j] = __ldg(cf + GS * GS + i * GS + j);
         }
-        *reinterpret_cast<float4*>(od + (size_t)rr * gm.C) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
+    const size_t base = (size_t)d * rows * gm.C + 4 * t.q;
+    const float* xd = x + base;
+    const float* gd = dout + base;
+    float* od = dx + base;
+    float* rd = dres + base;
+    const uint8_t* md = mask + (size_t)d * rows * t.C4 + t.q;
+    sweep_rows<UNROLL, false>(t, rows, [&](unsigned r) {
+      float4 v[UNROLL], q[UNROLL];
+      unsigned mb[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const unsigned rr = r + u * t.rpi;
+        if (rr < rows) {
+          v[u] = ldg4(xd + (size_t)rr * gm.C); q[u] = ldg4(gd + (size_t)rr * gm.C);
+          if constexpr (MASK) mb[u] = __ldg(md + (size_t)rr * t.C4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const unsigned rr = r + u * t.rpi;
+        if (rr < rows) {
+          const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, ge[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+          float o[4], zm[4];
+#pragma unroll
+          for (int s = 0; s < S::NSUB; ++s) {
+            float xi[GS], dz[GS];
+#pragma unroll
+            for (int c = 0; c < GS; ++c) { xi[c] = e[s * GS + c]; dz[c] = ge[s * GS + c]; }
+            if constexpr (RELU) {
+              float oi[GS];
+              apply_group<GS>(Wp[s], bp[s], xi, oi);
+#pragma unroll
+              for (int c = 0; c < GS; ++c) dz[c] = oi[c] > 0.f ? dz[c] : 0.f;
+            }
+            if constexpr (MASK) {
+#pragma unroll
+              for (int c = 0; c < GS; ++c) { dz[c] = ((mb[u] >> (s * GS + c)) & 1u) ? dz[c] : 0.f; zm[s * GS + c] = dz[c]; }
+            }
+#pragma unroll
+            for (int i = 0; i < GS; ++i) {
+              float a = cv[s][i];
+#pragma unroll
+              for (int j = i; j < GS; ++j) a = fmaf(A1[s][j * (j + 1) / 2 + i], dz[j], a);
+#pragma unroll
+              for (int j = 0; j < GS; ++j) {
+                const int hi = i > j ? i : j, lo = i > j ? j : i;
+                a = fmaf(Bm[s][hi * (hi + 1) / 2 + lo], xi[j], a);
+              }
+              o[s * GS + i] = a;
+            }
+          }
+          *reinterpret_cast<float4*>(od + (size_t)rr * gm.C) = make_float4(o[0], o[1], o[2], o[3]);
+          // gradient of the identity branch of relu(z + identity): the masked dout itself
+          if constexpr (MASK) { if (dres != nullptr) *reinterpret_cast<float4*>(rd + (size_t)rr * gm.C) = make_float4(zm[0], zm[1], zm[2], zm[3]); }
+        }
+      }
+    });
   }
 }
 
@@ -458,10 +522,15 @@ __global__ void __launch_bounds__(kT, 2) cl_bwd_apply_kernel(const float* __rest
   if ((E_) == 3) { constexpr int kEPI = 3; __VA_ARGS__; }                 \
   else if ((E_) == 1) { constexpr int kEPI = 1; __VA_ARGS__; }            \
   else { constexpr int kEPI = 0; __VA_ARGS__; }
+// backward: 7 = AFFINE with the ReLU mask of the residual tail read from the forward's byte map
+#define CL_EPI_BWD(E_, ...)                                               \
+  if ((E_) == 7) { constexpr int kEPI = 7; __VA_ARGS__; }                 \
+  else CL_EPI(E_, __VA_ARGS__)
 
-inline dim3 cl_grid(const Geom& gm, int nctas) {
+// grid.x = CTAs sweeping one domain, grid.y = column slabs, grid.z = 1 (domains one after the other) or D
+inline dim3 cl_grid(const Geom& gm, int nctas, int gz) {
   const int C4 = gm.C / 4, CW = C4 < kT ? C4 : kT;
-  return dim3(nctas, C4 / CW, gm.D);
+  return dim3(nctas, C4 / CW, gz);
 }
 
 }  // namespace
@@ -475,8 +544,8 @@ bool cl_supports(int C, int GS) {
 int cl_fwd_width(int C, int GS) { return (C / 4) * (4 / GS) * (GS + GS * (GS + 1) / 2); }
 int cl_bwd_width(int C, int GS) { return (C / 4) * (4 / GS) * (GS * GS + GS); }
 
-void cl_stats(const float* x, const Geom& gm, int nctas, float* partial, float* shift, cudaStream_t st) {
-  CL_GS(gm.GS, (cl_stats_kernel<kGS><<<cl_grid(gm, nctas), kT, 0, st>>>(x, gm, partial, shift)));
+void cl_stats(const float* x, const Geom& gm, int nctas, int gz, float* partial, float* shift, cudaStream_t st) {
+  CL_GS(gm.GS, (cl_stats_kernel<kGS><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, gm, partial, shift)));
 }
 void cl_vec_reduce(const float* partial, int nrows, int W, int D, int S, float* out, cudaStream_t st) {
   vec_reduce_kernel<<<dim3((W + 63) / 64, D, S), 256, 0, st>>>(partial, nrows, W, out);
@@ -484,24 +553,25 @@ void cl_vec_reduce(const float* partial, int nrows, int W, int D, int S, float* 
 void cl_fwd_finalize(const float* red, int S, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st) {
   CL_GS(gm.GS, (cl_fwd_finalize_kernel<kGS><<<(gm.G + 63) / 64, dim3(64, gm.D), 0, st>>>(red, S, shift, gm, fin)));
 }
-void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
-              const float* gamma, const float* beta, const float* residual, cudaStream_t st) {
+void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
+              const float* gamma, const float* beta, const float* residual, uint8_t* mask, cudaStream_t st) {
   if (epi == 7) {
-    CL_GS(gm.GS, (cl_apply_kernel<kGS, 7><<<cl_grid(gm, nctas), kT, 0, st>>>(x, y, gm, mean, w, gamma, beta, residual)));
+    CL_GS(gm.GS, (cl_apply_kernel<kGS, 7><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, y, gm, mean, w, gamma, beta, residual, mask)));
     return;
   }
-  CL_GS(gm.GS, CL_EPI(epi, (cl_apply_kernel<kGS, kEPI><<<cl_grid(gm, nctas), kT, 0, st>>>(x, y, gm, mean, w, gamma, beta, nullptr))));
+  CL_GS(gm.GS, CL_EPI(epi, (cl_apply_kernel<kGS, kEPI><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, y, gm, mean, w, gamma, beta, nullptr, nullptr))));
 }
-void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
-                   const float* gamma, const float* beta, float* partial, cudaStream_t st) {
-  CL_GS(gm.GS, CL_EPI(epi, (cl_bwd_reduce_kernel<kGS, kEPI><<<cl_grid(gm, nctas), kT, 0, st>>>(x, dout, gm, mean, w, gamma, beta, partial))));
+void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
+                   const float* gamma, const float* beta, const uint8_t* mask, float* partial, cudaStream_t st) {
+  CL_GS(gm.GS, CL_EPI_BWD(epi, (cl_bwd_reduce_kernel<kGS, kEPI><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, dout, gm, mean, w, gamma, beta, mask, partial))));
 }
 void cl_bwd_finalize(const float* red, int S, const Geom& gm, const BwdFin& fin, cudaStream_t st) {
   CL_GS(gm.GS, (cl_bwd_finalize_kernel<kGS><<<(gm.G + 63) / 64, dim3(64, gm.D), 0, st>>>(red, S, gm, fin)));
 }
-void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, int epi, const float* coef,
-                  const float* mean, const float* w, const float* gamma, const float* beta, cudaStream_t st) {
-  CL_GS(gm.GS, CL_EPI(epi, (cl_bwd_apply_kernel<kGS, kEPI><<<cl_grid(gm, nctas), kT, 0, st>>>(x, dout, dx, gm, coef, mean, w, gamma, beta))));
+void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, int gz, int epi, const float* coef,
+                  const float* mean, const float* w, const float* gamma, const float* beta, const uint8_t* mask, float* dres,
+                  cudaStream_t st) {
+  CL_GS(gm.GS, CL_EPI_BWD(epi, (cl_bwd_apply_kernel<kGS, kEPI><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, dout, dx, gm, coef, mean, w, gamma, beta, mask, dres))));
 }
 
 }  // namespace dwt

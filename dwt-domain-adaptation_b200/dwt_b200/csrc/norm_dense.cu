@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) fwd_factor_kernel(const float* __restrict
   float* sT = sW + kMat;           // scratch of the inverse
   float* sC = sT + kMat;           // un-shrunk covariance (for the EMA)
   __shared__ float sCol[2][kSB], sPiv[2], sMean[kSB];
-  __shared__ int sBad;
+  __shared__ int sBad, sBadDom;
   const int g = blockIdx.x, GS = gm.GS, nb = kSB / GS, sb = g / nb, o = (g % nb) * GS;
   const Blk t(GS);
   const int SB = (gm.C + kSB - 1) / kSB;
@@ -235,8 +235,9 @@ __global__ void __launch_bounds__(256) fwd_factor_kernel(const float* __restrict
         }
         a[r][s] = v;
       }
+    if (threadIdx.x == 0) sBadDom = 0;
     __syncthreads();
-    if (!cholesky_blocked(a, GS, t, sCol, sPiv)) sBad = 1;
+    if (!cholesky_blocked(a, GS, t, sCol, sPiv)) { sBad = 1; sBadDom = 1; }
     if (t.act) {
 #pragma unroll
       for (int r = 0; r < 4; ++r)
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(256) fwd_factor_kernel(const float* __restrict
     __syncthreads();
     tri_inverse(sL, sW, sT, GS);
     for (int e = threadIdx.x; e < GS * GS; e += blockDim.x) f.save_w[gbase + e] = sW[(e / GS) * LDS + e % GS];
-    if (G && f.update_running) {
+    if (G && f.update_running && !sBadDom) {       // a non-PD batch covariance never reaches the running buffers
       const float m = f.momentum, k = 1.f - f.momentum;
       for (int e = threadIdx.x; e < GS * GS; e += blockDim.x) {
         float* p = f.rcov[d] + (size_t)g * GS * GS + e;
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(256) fwd_factor_kernel(const float* __restrict
     }
     __syncthreads();      // also orders this domain's buffer writes before the next domain's reads (aliasing)
   }
-  if (threadIdx.x == 0 && sBad) atomicOr(f.status, 1);
+  if (threadIdx.x == 0 && sBad) atomicOr(f.status, DWT_STATUS_NOT_PD);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -67,16 +67,17 @@ int tc_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, i
 bool cl_supports(int C, int GS);
 int cl_fwd_width(int C, int GS);
 int cl_bwd_width(int C, int GS);
-void cl_stats(const float* x, const Geom& gm, int nctas, float* partial, float* shift, cudaStream_t st);
+void cl_stats(const float* x, const Geom& gm, int nctas, int gz, float* partial, float* shift, cudaStream_t st);
 void cl_vec_reduce(const float* partial, int nrows, int W, int D, int S, float* out, cudaStream_t st);
 void cl_fwd_finalize(const float* red, int S, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st);
-void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
-              const float* gamma, const float* beta, const float* residual, cudaStream_t st);
-void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas, int epi, const float* mean, const float* w,
-                   const float* gamma, const float* beta, float* partial, cudaStream_t st);
+void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
+              const float* gamma, const float* beta, const float* residual, uint8_t* mask, cudaStream_t st);
+void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
+                   const float* gamma, const float* beta, const uint8_t* mask, float* partial, cudaStream_t st);
 void cl_bwd_finalize(const float* red, int S, const Geom& gm, const BwdFin& fin, cudaStream_t st);
-void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, int epi, const float* coef,
-                  const float* mean, const float* w, const float* gamma, const float* beta, cudaStream_t st);
+void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, int gz, int epi, const float* coef,
+                  const float* mean, const float* w, const float* gamma, const float* beta, const uint8_t* mask, float* dres,
+                  cudaStream_t st);
 
 // MEC loss (mec.cu)
 // paired target augmentation (augment.cu); mean / stdv are HOST arrays of 3
@@ -84,7 +85,7 @@ void augment_pair_launch(const uint8_t* images, int B, int SH, int SW, int CR, c
                          const uint8_t* flip, const float* affine, const float* mean, const float* stdv,
                          float* out_plain, float* out_aug, int nhwc, cudaStream_t st);
 void head_loss_launch(const float* logits, const long long* labels, int B, int K, float lambda, float* losses,
-                      float* grad, cudaStream_t st);
+                      float* grad, int* status, cudaStream_t st);
 void mec_launch(const float* x, const float* y, int N, int K, float* loss, float* gx, float* gy, cudaStream_t st);
 
 }  // namespace dwt

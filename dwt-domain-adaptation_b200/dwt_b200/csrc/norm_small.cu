@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(kThreads, (GS * VEC >= 16) ? 3 : 4) small_stat
       const float cij = a[GS + i * (i + 1) / 2 + j] * invM - (a[i] * invM) * (a[j] * invM);
       cov[i][j] = cij; cov[j][i] = cij;
     }
-  factor_thread<GS>(gm, fin, d, tm.g, mean, cov, true);
-  ema_thread<GS>(gm, fin, d, tm.g, mean, cov);
+  const bool bad = factor_thread<GS>(gm, fin, d, tm.g, mean, cov, true);
+  ema_thread<GS>(gm, fin, d, tm.g, mean, cov, bad);
 }
 
 // Eval mode: W and mean straight from the running buffers (whitening.py:42-43,50-53).

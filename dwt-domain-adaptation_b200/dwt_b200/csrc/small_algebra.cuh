@@ -72,7 +72,7 @@ __device__ __forceinline__ void load_forward_map(const float* save_w_g, const fl
 // single-thread finalize steps (GS <= 4, everything in registers)
 // ------------------------------------------------------------------------------------------
 template <int GS>
-__device__ __forceinline__ void factor_thread(const Geom& gm, const FwdFin& f, int d, int g, const float (&mean)[GS],
+__device__ __forceinline__ bool factor_thread(const Geom& gm, const FwdFin& f, int d, int g, const float (&mean)[GS],
                                               const float (&cov)[GS][GS], bool store_cov) {
   const size_t gbase = ((size_t)d * gm.G + g) * GS * GS;
   float L[GS][GS], W[GS][GS];
@@ -99,7 +99,8 @@ __device__ __forceinline__ void factor_thread(const Geom& gm, const FwdFin& f, i
 #pragma unroll
       for (int j = k + 1; j <= i; ++j) L[i][j] -= L[i][k] * L[j][k];
   }
-  if (bad) atomicOr(f.status, 1);
+  if (bad) atomicOr(f.status, DWT_STATUS_NOT_PD);
+  if (store_cov) f.bad[d * gm.G + g] = bad ? 1 : 0;
 #pragma unroll
   for (int j = 0; j < GS; ++j) {
     W[j][j] = 1.f / L[j][j];
@@ -115,17 +116,19 @@ __device__ __forceinline__ void factor_thread(const Geom& gm, const FwdFin& f, i
   for (int i = 0; i < GS; ++i)
 #pragma unroll
     for (int j = 0; j < GS; ++j) f.save_w[gbase + i * GS + j] = W[i][j];
+  return bad;
 }
 
 // EMA of the running buffers by one thread, domains in order.  With several
 // domains the thread that finalizes the LAST domain of group g applies all D updates.
 template <int GS>
 __device__ __forceinline__ void ema_thread(const Geom& gm, const FwdFin& f, int d_self, int g,
-                                           const float (&mean)[GS], const float (&cov)[GS][GS]) {
+                                           const float (&mean)[GS], const float (&cov)[GS][GS], bool bad_self) {
   if (!f.update_running) return;
   const float m = f.momentum, k = 1.f - f.momentum;
   if (gm.D == 1 || f.aliased == 0) {
     // this domain owns its buffers: update them directly from registers, no cross-CTA traffic
+    if (bad_self) return;
     float* rc = f.rcov[d_self] + (size_t)g * GS * GS;
     float* rm = f.rmean[d_self] + g * GS;
 #pragma unroll
@@ -152,6 +155,7 @@ __device__ __forceinline__ void ema_thread(const Geom& gm, const FwdFin& f, int 
 #pragma unroll
     for (int e = 0; e < GS; ++e) u[e] = rm[e];
     for (int d = 0; d < gm.D; ++d) {
+      if (__ldcg(f.bad + d * gm.G + g)) continue;
       const float* cv = f.save_cov + ((size_t)d * gm.G + g) * GS * GS;
       const float* mu = f.save_mean + (size_t)d * gm.C + g * GS;
 #pragma unroll
@@ -166,6 +170,7 @@ __device__ __forceinline__ void ema_thread(const Geom& gm, const FwdFin& f, int 
     return;
   }
   for (int d = 0; d < gm.D; ++d) {       // mixed aliasing: plain ordered read-modify-write
+    if (__ldcg(f.bad + d * gm.G + g)) continue;
     const float* cv = f.save_cov + ((size_t)d * gm.G + g) * GS * GS;
     const float* mu = f.save_mean + (size_t)d * gm.C + g * GS;
     float* rc = f.rcov[d] + (size_t)g * GS * GS;

@@ -27,6 +27,17 @@ def _dense(x: torch.Tensor, group_size: int):
     return x, n, c, hw, nhwc
 
 
+def _check_param(name, t, numel):
+    """The C ABI takes raw pointers: a strided or mis-sized statistics / affine tensor would be read or written out
+    of bounds on the device, where the reference raises a shape error.  Validate before taking data_ptr()."""
+    if t is None:
+        return
+    if t.numel() != numel:
+        raise ValueError(f"{name} has {t.numel()} elements, expected {numel}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous (it is written / read through a raw pointer)")
+
+
 class _NormFunction(torch.autograd.Function):
     """Shared by whitening (kind='whiten') and domain batch norm (kind='bn').
 
@@ -45,6 +56,11 @@ class _NormFunction(torch.autograd.Function):
             raise ValueError(f"batch of {n_all} does not split into {n_domains} domains")
         n = n_all // n_domains
         dev = nv.require_cuda(x, gamma, beta, residual, *[t for pair in running for t in pair])
+        for d, (rm_t, rv_t) in enumerate(running):
+            _check_param(f"running mean of domain {d}", rm_t, c)
+            _check_param(f"running second moment of domain {d}", rv_t, c * gs)
+        _check_param("gamma / weight", gamma, c)
+        _check_param("beta / bias", beta, c)
         epi = nv.EPI_NONE
         if residual is not None:
             if gamma is None or not relu or residual.shape != x.shape:
@@ -56,6 +72,9 @@ class _NormFunction(torch.autograd.Function):
         else:
             gamma_c = beta_c = None
         y = torch.empty_like(x)                      # keeps x's memory format
+        # residual tail on the channels-last kernels: the apply pass leaves one byte per float4 with the four
+        # (out > 0) bits, which is all the backward needs of the output
+        mask = torch.empty(x.numel() // 4, dtype=torch.uint8, device=dev) if (residual is not None and nhwc) else None
         save_mean = torch.empty(n_domains, c, dtype=torch.float32, device=dev)
         save_w = torch.empty(n_domains, c // gs, gs, gs, dtype=torch.float32, device=dev)
         ws = nv.workspace(dev, n, c, hw, gs, n_domains)
@@ -65,28 +84,48 @@ class _NormFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             if kind == "whiten":
                 rc = lib.dwt_whiten_fwd(nv.ptr(x), nv.ptr(y), n, c, hw, gs, n_domains, mode | layout, eps, momentum,
-                                        int(update_running), rm, rv, nv.ptr(gamma_c), nv.ptr(beta_c), nv.ptr(residual), epi,
-                                        nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
+                                        int(update_running), rm, rv, nv.ptr(gamma_c), nv.ptr(beta_c), nv.ptr(residual),
+                                        nv.ptr(mask), epi, nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(ws), ws.numel(),
+                                        nv.stream_ptr(dev))
             else:
                 rc = lib.dwt_bn_fwd(nv.ptr(x), nv.ptr(y), n, c, hw, n_domains, mode | layout, eps, momentum,
-                                    int(update_running), rm, rv, nv.ptr(gamma_c), nv.ptr(beta_c), nv.ptr(residual), epi,
-                                    nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
+                                    int(update_running), rm, rv, nv.ptr(gamma_c), nv.ptr(beta_c), nv.ptr(residual),
+                                    nv.ptr(mask), epi, nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(ws), ws.numel(),
+                                    nv.stream_ptr(dev))
         nv.check(rc)
-        if residual is not None:
-            # backward of relu(z + residual): dz = dout * (out > 0) is also the residual's gradient; the norm's own
-            # backward then runs on dz with the plain affine epilogue -- same bytes as masking inside the kernels
+        nv.poll_status(dev)
+        if update_running and mode == nv.MODE_TRAIN:
+            # the kernels wrote the running buffers in place behind autograd's back: bump their version counters so a
+            # graph that saved one of them notices (the reference's in-place EMA, whitening.py:58-59, does the same)
+            seen = set()
+            for pair in running:
+                for buf in pair:
+                    if buf is not None and id(buf) not in seen:
+                        seen.add(id(buf))
+                        torch.autograd.graph.increment_version(buf)
+        # backward of relu(z + residual): dz = dout * (out > 0) is also the residual's gradient
+        ctx.residual_mode = None
+        if mask is not None:
+            # channels-last: both backward kernels mask dout with the saved bits, bwd_apply also writes dz
+            ctx.save_for_backward(x, save_mean, save_w, gamma_c, beta_c, mask)
+            ctx.residual_mode = "mask"
+        elif residual is not None:
+            # NCHW: dz is formed by one ATen pass from the saved output; the kernels then run the plain affine epilogue
             ctx.save_for_backward(x, save_mean, save_w, gamma_c, beta_c, y)
             epi = nv.EPI_AFFINE
+            ctx.residual_mode = "aten"
         else:
             ctx.save_for_backward(x, save_mean, save_w, gamma_c, beta_c)
-        ctx.has_residual = residual is not None
         ctx.cfg = (kind, gs, n_domains, mode | layout, eps, epi, n, c, hw, None if gamma is None else gamma.shape)
         return y
 
     @staticmethod
     def backward(ctx, dout):
         lib = nv.lib()
-        if ctx.has_residual:
+        mask = None
+        if ctx.residual_mode == "mask":
+            x, save_mean, save_w, gamma_c, beta_c, mask = ctx.saved_tensors
+        elif ctx.residual_mode == "aten":
             x, save_mean, save_w, gamma_c, beta_c, out = ctx.saved_tensors
             dout = torch.ops.aten.threshold_backward(dout, out, 0)
         else:
@@ -96,18 +135,25 @@ class _NormFunction(torch.autograd.Function):
         dev = nv.require_cuda(dout)
         dx = torch.empty_like(x)
         want_affine = gamma_c is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
-        d_res = dout if (ctx.has_residual and ctx.needs_input_grad[3]) else None
+        d_res = None
+        if ctx.needs_input_grad[3]:
+            if ctx.residual_mode == "mask":
+                d_res = torch.empty_like(x)
+            elif ctx.residual_mode == "aten":
+                d_res = dout
         dgamma = torch.empty(c, dtype=torch.float32, device=dev) if want_affine else None
         dbeta = torch.empty(c, dtype=torch.float32, device=dev) if want_affine else None
         ws = nv.workspace(dev, n, c, hw, gs, n_domains)
         with torch.cuda.device(dev):
             if kind == "whiten":
                 rc = lib.dwt_whiten_bwd(nv.ptr(x), nv.ptr(dout), nv.ptr(dx), n, c, hw, gs, n_domains, mode, eps,
-                                        nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(gamma_c), nv.ptr(beta_c), epi,
+                                        nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(gamma_c), nv.ptr(beta_c), nv.ptr(mask),
+                                        nv.ptr(d_res) if mask is not None else None, epi,
                                         nv.ptr(dgamma), nv.ptr(dbeta), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
             else:
                 rc = lib.dwt_bn_bwd(nv.ptr(x), nv.ptr(dout), nv.ptr(dx), n, c, hw, n_domains, mode,
-                                    nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(gamma_c), nv.ptr(beta_c), epi,
+                                    nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(gamma_c), nv.ptr(beta_c), nv.ptr(mask),
+                                    nv.ptr(d_res) if mask is not None else None, epi,
                                     nv.ptr(dgamma), nv.ptr(dbeta), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
         nv.check(rc)
         if want_affine:
@@ -164,8 +210,9 @@ class _HeadLossFunction(torch.autograd.Function):
         grad = torch.empty_like(logits)
         with torch.cuda.device(dev):
             rc = lib.dwt_head_loss_fwd_bwd(nv.ptr(logits), nv.ptr(labels), labels.shape[0], logits.shape[1], float(lam),
-                                           nv.ptr(losses), nv.ptr(grad), nv.stream_ptr(dev))
+                                           nv.ptr(losses), nv.ptr(grad), nv.status_ptr(dev), nv.stream_ptr(dev))
         nv.check(rc)
+        nv.poll_status(dev)
         ctx.save_for_backward(grad)
         ctx.mark_non_differentiable(losses)
         return losses[0], losses

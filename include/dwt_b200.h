@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define DWT_B200_ABI_VERSION 3
+#define DWT_B200_ABI_VERSION 4
 #define DWT_MAX_DOMAINS 4
 #define DWT_MAX_GROUP_SIZE 64
 
@@ -87,9 +87,14 @@ DWT_API const char *dwt_last_error(void);
  * calls issued on ONE stream.  Size for the largest call the caller will make. */
 DWT_API size_t dwt_workspace_bytes(int64_t N, int64_t C, int64_t HW, int group_size, int n_domains);
 
-/* Device status word (first int of the workspace): 0 = ok, bit 0 = a covariance
- * was not positive definite (the reference raises from torch.cholesky here).
- * Read it with a device->host copy when you want to know; nothing syncs for it. */
+/* Device status word (first int of the workspace): 0 = ok; bits below are OR-ed in by the kernels and stay
+ * set until the caller clears the word.  Read it with a device->host copy when you want to know; nothing
+ * syncs for it (dwt_b200.raise_on_status() in the Python layer polls it every k calls and raises). */
+#define DWT_STATUS_NOT_PD 1    /* a batch (or running) covariance was not positive definite: the reference raises
+                                  from torch.cholesky (whitening.py:53); here W is NaN for that group and that
+                                  domain's running-statistics update is skipped                                  */
+#define DWT_STATUS_BAD_LABEL 2 /* dwt_head_loss_fwd_bwd: a label outside [0, K) other than -100 (F.nll_loss would
+                                  device-assert); the row is dropped like an ignored one, never dereferenced     */
 
 /*
  * Whitening forward.
@@ -100,6 +105,9 @@ DWT_API size_t dwt_workspace_bytes(int64_t N, int64_t C, int64_t HW, int group_s
  *   save_w          [n_domains, C/gs, gs, gs] W = inverse(cholesky((1-eps) cov + eps I))
  *   gamma, beta     [C] or NULL (epilogue)
  *   residual        same shape/layout as x, or NULL (DWT_EPI_RESIDUAL)
+ *   relu_mask       NULL, or (channels-last RESIDUAL epilogue) one byte per float4 of the output in memory order
+ *                   [n_domains*N*HW*C/4]: bit k = (out[4i+k] > 0).  The backward needs it because the
+ *                   pre-activation cannot be recomputed without the residual.
  * TRAIN: batch mean/cov; when update_running, the EMA r = (1-m) r + m stat is applied
  * domain by domain in order (so aliased buffers see s, then t, then t_aug --
  * SURVEY.md H5), on the UN-shrunk covariance (whitening.py:57-59).
@@ -108,19 +116,23 @@ DWT_API size_t dwt_workspace_bytes(int64_t N, int64_t C, int64_t HW, int group_s
 DWT_API int dwt_whiten_fwd(const float *x, float *y, int64_t N, int64_t C, int64_t HW, int group_size,
                    int n_domains, int mode, float eps, float momentum, int update_running,
                    float *const *running_mean, float *const *running_cov, const float *gamma,
-                   const float *beta, const float *residual, int epilogue, float *save_mean, float *save_w,
-                   void *workspace, size_t workspace_bytes, dwt_stream_t stream);
+                   const float *beta, const float *residual, uint8_t *relu_mask, int epilogue, float *save_mean,
+                   float *save_w, void *workspace, size_t workspace_bytes, dwt_stream_t stream);
 
 /*
  * Whitening backward (closed form).  dout is the gradient of the
  * forward's output (after the epilogue, if any).  dgamma/dbeta [C] are written
  * (summed over domains) when the epilogue has AFFINE; pass NULL otherwise.
+ * Epilogue AFFINE|RELU|RESIDUAL (channels-last only): dout is the gradient of relu(z + residual); the ReLU mask is
+ * read from the forward's relu_mask and, when dresidual is not NULL, the masked gradient dout * (out > 0) -- the
+ * gradient of the identity branch -- is written there in the same pass (resnet50_dwt_mec_officehome.py:239-240).
+ * Without RESIDUAL pass relu_mask = dresidual = NULL.
  */
 DWT_API int dwt_whiten_bwd(const float *x, const float *dout, float *dx, int64_t N, int64_t C, int64_t HW,
                    int group_size, int n_domains, int mode, float eps, const float *save_mean,
-                   const float *save_w, const float *gamma, const float *beta, int epilogue,
-                   float *dgamma, float *dbeta, void *workspace, size_t workspace_bytes,
-                   dwt_stream_t stream);
+                   const float *save_w, const float *gamma, const float *beta, const uint8_t *relu_mask,
+                   float *dresidual, int epilogue, float *dgamma, float *dbeta, void *workspace,
+                   size_t workspace_bytes, dwt_stream_t stream);
 
 /*
  * Domain batch norm (F.batch_norm semantics): biased batch variance normalises,
@@ -131,13 +143,13 @@ DWT_API int dwt_whiten_bwd(const float *x, const float *dout, float *dx, int64_t
 DWT_API int dwt_bn_fwd(const float *x, float *y, int64_t N, int64_t C, int64_t HW, int n_domains, int mode,
                float eps, float factor, int update_running, float *const *running_mean,
                float *const *running_var, const float *weight, const float *bias, const float *residual,
-               int epilogue, float *save_mean, float *save_invstd, void *workspace, size_t workspace_bytes,
-               dwt_stream_t stream);
+               uint8_t *relu_mask, int epilogue, float *save_mean, float *save_invstd, void *workspace,
+               size_t workspace_bytes, dwt_stream_t stream);
 
 DWT_API int dwt_bn_bwd(const float *x, const float *dout, float *dx, int64_t N, int64_t C, int64_t HW,
                int n_domains, int mode, const float *save_mean, const float *save_invstd,
-               const float *weight, const float *bias, int epilogue, float *dweight, float *dbias,
-               void *workspace, size_t workspace_bytes, dwt_stream_t stream);
+               const float *weight, const float *bias, const uint8_t *relu_mask, float *dresidual, int epilogue,
+               float *dweight, float *dbias, void *workspace, size_t workspace_bytes, dwt_stream_t stream);
 
 /*
  * Min-Entropy-Consensus loss, forward and both gradients in one launch.
@@ -152,9 +164,12 @@ DWT_API int dwt_mec_fwd_bwd(const float *x, const float *y, int64_t N, int64_t K
  *   logits [3B, K] = source | target | target-aug, labels [B] (int64)
  *   total = mean_n NLL(log_softmax(source_n), label_n) + lambda * MEC(target, target-aug)
  * losses [3] = total, classification, lambda*MEC ;  grad [3B, K] = d total / d logits.
+ * Labels as in F.nll_loss: -100 rows are ignored (dropped from the sum and the mean's denominator); any other label
+ * outside [0, K) sets DWT_STATUS_BAD_LABEL in *status (device int, may be NULL: e.g. the workspace's status word)
+ * and is dropped too -- never dereferenced.
  */
 DWT_API int dwt_head_loss_fwd_bwd(const float *logits, const int64_t *labels, int64_t B, int64_t K, float lambda,
-                          float *losses, float *grad, dwt_stream_t stream);
+                          float *losses, float *grad, int *status, dwt_stream_t stream);
 
 /*
  * Paired target augmentation: both views the reference's loader derives from one image

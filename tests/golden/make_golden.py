@@ -156,8 +156,10 @@ def bn_cases():
                         **{k: v.numpy() for k, v in out.items()})
 
 
-def resnet_case():
-    """Full reference model (resnet50_dwt_mec_officehome.py ResNet) on a tiny synthetic batch."""
+def resnet_case(size=96, name="resnet_tiny"):
+    """Full reference model (resnet50_dwt_mec_officehome.py ResNet) on a small synthetic batch.
+    size=96: tiny spatial sites; size=224: the real site shapes of BASELINE configs[2]
+    (112^2 / 56^2 / 28^2 / 14^2 / 7^2) at 4 images per domain."""
     from harness.synth import synth_batch, synth_state_dict
     cwd = os.getcwd()
     os.chdir(REF)
@@ -165,7 +167,7 @@ def resnet_case():
     import resnet50_dwt_mec_officehome as script
     os.chdir(cwd)
     sd = synth_state_dict(seed=1)
-    x, labels = synth_batch(seed=2, per_domain=4, size=96)
+    x, labels = synth_batch(seed=2, per_domain=4, size=size)
     model = script.ResNet(script.Bottleneck, [3, 4, 6, 3], {k: v.clone() for k, v in sd.items()})
     model.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
     model.train()
@@ -189,7 +191,7 @@ def resnet_case():
     model.eval()
     with torch.no_grad():
         out["logits_eval"] = model(x)
-    np.savez_compressed(os.path.join(HERE, "resnet_tiny.npz"), torch=torch.__version__,
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), torch=torch.__version__,
                         **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
 
 
@@ -200,4 +202,5 @@ if __name__ == "__main__":
     mec_cases()
     bn_cases()
     resnet_case()
+    resnet_case(size=224, name="resnet_224")
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
