@@ -129,11 +129,11 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- model
-def build_model(layers, device, site_mode, seed=1, channels_last=False):
+def build_model(layers, device, site_mode, seed=1, channels_last=False, stem_pad=0):
     from harness.resnet50_dwt import build_resnet50_dwt
     from harness.synth import synth_state_dict
     sd = {k: v.to(device) for k, v in synth_state_dict(seed=seed).items()}
-    model = build_resnet50_dwt(sd, layers, site_mode=site_mode, channels_last=channels_last).to(device)
+    model = build_resnet50_dwt(sd, layers, site_mode=site_mode, channels_last=channels_last, stem_pad=stem_pad).to(device)
     return model.train()
 
 
@@ -147,35 +147,83 @@ def make_optimizer(model):
 
 class FlatGradAllReduce:
     """Plain data parallelism: every parameter's .grad is a view into ONE flat fp32 buffer
-    (94.6 MB for ResNet-50-DWT); after backward a single all-reduce averages it over the ranks (NCCL over
-    NVLink on the B200 box, gloo in the CPU test).  One collective per step, no hooks, no bucketing logic --
-    so the whole step, collective included, can be captured into a CUDA graph.  Whitening / BN statistics are
-    never exchanged: every rank normalises its own minibatch."""
+    (94.6 MB for ResNet-50-DWT), averaged over the ranks by NCCL over NVLink (gloo in the CPU test).  Whitening / BN
+    statistics are never exchanged: every rank normalises its own minibatch.
 
-    def __init__(self, model, world):
+    The buffer is cut into `segments` contiguous pieces along the layer order and each piece is all-reduced as soon
+    as backward has produced its last gradient (a post-accumulate hook per parameter counts them down): backward
+    runs layer4 -> stem, so the big late-layer pieces (layer4 + fc = 60 MB, layer3 = 28 MB) travel while the earlier
+    layers are still back-propagating and only the small stem / layer1 / layer2 piece (6 MB) is exposed at the end.
+    The collectives are issued asynchronously on NCCL's own stream (async_op) and joined in reduce(); no Python runs
+    at replay time -- the whole step, collectives and cross-stream edges included, is captured into the CUDA graph.
+    segments=1 is the round-1 behaviour: one all-reduce after backward."""
+
+    def __init__(self, model, world, segments=3):
         import torch.distributed as dist
         self.world, self.dist = world, dist
-        params = [p for p in model.parameters() if p.requires_grad]
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        params = [p for _, p in named]
         total = sum(p.numel() for p in params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
-        off = 0
+        off, offsets = 0, []
         for p in params:
             p.grad = self.flat[off:off + p.numel()].as_strided(p.shape, p.stride())   # same memory format as p
+            offsets.append(off)
             off += p.numel()
+        # segment boundaries in layer order: [stem, layer1, layer2 | layer3 | layer4, fc_out] (fewer when asked)
+        cuts = [0]
+        if segments >= 3:
+            cuts += [i for i, (n, _) in enumerate(named) if n.startswith("layer3.")][:1]
+        if segments >= 2:
+            cuts += [i for i, (n, _) in enumerate(named) if n.startswith("layer4.")][:1]
+        cuts = sorted(set(cuts)) + [len(params)]
+        self.ranges, self.seg_of = [], {}
+        for k in range(len(cuts) - 1):
+            a, b = cuts[k], cuts[k + 1]
+            self.ranges.append((offsets[a], off if b == len(params) else offsets[b], b - a))
+            for p in params[a:b]:
+                self.seg_of[id(p)] = k
+        self.pending = [r[2] for r in self.ranges]
+        self.works = []
+        self.launched = [False] * len(self.ranges)
         if world > 1:
             for p in params:                         # identical by construction (seeded); make it explicit
                 dist.broadcast(p.data, 0)
+            if len(self.ranges) > 1:
+                for p in params:
+                    p.register_post_accumulate_grad_hook(self._on_grad)
 
     def zero(self):
         self.flat.zero_()
+        self.pending = [r[2] for r in self.ranges]
+        self.launched = [False] * len(self.ranges)
+        self.works = []
+
+    def _on_grad(self, p):
+        k = self.seg_of[id(p)]
+        self.pending[k] -= 1
+        if self.pending[k] == 0:
+            self._launch(k)
+
+    def _launch(self, k):
+        a, b, _ = self.ranges[k]
+        self.launched[k] = True
+        seg = self.flat[a:b]
+        if self.flat.is_cuda:
+            self.works.append(self.dist.all_reduce(seg, op=self.dist.ReduceOp.AVG, async_op=True))
+        else:
+            self.works.append(self.dist.all_reduce(seg, op=self.dist.ReduceOp.SUM, async_op=True))
 
     def reduce(self):
-        if self.world > 1:
-            if self.flat.is_cuda:
-                self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.AVG)
-            else:
-                self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM)
-                self.flat.div_(self.world)
+        if self.world <= 1:
+            return
+        for k in range(len(self.ranges) - 1, -1, -1):   # whatever backward did not complete (unused parameters), in a
+            if not self.launched[k]:                     # fixed order on every rank
+                self._launch(k)
+        for w in self.works:
+            w.wait()                                 # CUDA: the compute stream waits on NCCL's stream, the host does not
+        if not self.flat.is_cuda:
+            self.flat.div_(self.world)
 
 
 def train_step(model, mec, opt, images, labels, sync=None, head=None):
@@ -276,7 +324,9 @@ def workload_config(args, per_domain, site_mode):
     return {"workload": "ResNet-50-DWT synthetic Office-Home 224x224, train step = fwd + NLL + 0.1*MEC + bwd + SGD",
             "per_domain_batch": per_domain, "images_per_gpu": 3 * per_domain, "global_images": 3 * per_domain * args.gpus,
             "group_size": 4, "site_mode": site_mode, "memory_format": getattr(args, "memory_format", "nchw"),
-            "parallelism": f"dp{args.gpus}", "grad_sync": "one flat NCCL all-reduce (AVG) per step",
+            "parallelism": f"dp{args.gpus}",
+            "grad_sync": (f"flat fp32 gradient buffer, NCCL all-reduce (AVG) in {getattr(args, 'grad_segments', 1)} segment(s) "
+                          "issued as backward completes them (layer4+fc, layer3, rest), overlapped with the remaining backward"),
             "l2": "no explicit flush: per-step working set (activations) is tens of GB >> 126 MB L2",
             "launch": "CUDA-graph replay of the whole step" if getattr(args, "cuda_graph", False) and getattr(args, "impl", "ours") == "ours" else "eager"}
 
@@ -418,9 +468,9 @@ def run_ours(args):
         return
 
     nhwc = args.memory_format == "nhwc"
-    model = build_model(dwt_b200, device, args.site_mode, channels_last=nhwc)
+    model = build_model(dwt_b200, device, args.site_mode, channels_last=nhwc, stem_pad=args.stem_pad)
     net = model
-    sync = FlatGradAllReduce(model, world) if distributed else None    # one GPU: plain autograd .grad tensors
+    sync = FlatGradAllReduce(model, world, segments=args.grad_segments) if distributed else None   # one GPU: plain .grad tensors
     opt = make_optimizer(model)
     mec = dwt_b200.MinEntropyConsensusLoss(NUM_CLASSES, device)
     head = dwt_b200.HeadLoss(NUM_CLASSES, LAMBDA_MEC)
@@ -741,6 +791,10 @@ def main():
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
                     help="time the eager step instead of a CUDA-graph replay of it")
     ap.add_argument("--sites-out", default="", help="write the per-site kernel table (JSON) here")
+    ap.add_argument("--stem-pad", type=int, default=0, choices=[0, 4, 8],
+                    help="zero-pad the 3-channel image (and the stem weight) to this many channels for cuDNN")
+    ap.add_argument("--grad-segments", type=int, default=3, choices=[1, 2, 3],
+                    help="pieces the flat gradient buffer is all-reduced in (1 = one collective after backward)")
     ap.add_argument("--micro-n", type=int, default=256)
     ap.add_argument("--micro-gs", type=int, default=64)
     args = ap.parse_args()

@@ -10,8 +10,9 @@ from .augment import PairedAugment, draw_params
 from .batch_norm import BatchNorm1d, BatchNorm2d, BatchNorm3d
 from .consensus_loss import HeadLoss, MinEntropyConsensusLoss
 from .fused import DomainTripleNorm
+from .pooling import MaxPool2d
 from .whitening import WTransform2d
 
 __all__ = ["WTransform2d", "BatchNorm1d", "BatchNorm2d", "BatchNorm3d", "MinEntropyConsensusLoss",
-           "DomainTripleNorm", "HeadLoss", "PairedAugment", "draw_params", "raise_on_status", "check_status",
+           "DomainTripleNorm", "HeadLoss", "MaxPool2d", "PairedAugment", "draw_params", "raise_on_status", "check_status",
            "NotPositiveDefiniteError", "_native"]

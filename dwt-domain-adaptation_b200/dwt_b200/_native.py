@@ -55,6 +55,10 @@ _SIGNATURES = {
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_float_p,
                                         ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _c_float_p,
                                         _c_float_p, ctypes.c_int, ctypes.c_void_p]),
+    "dwt_maxpool_fwd": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                       ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "dwt_maxpool_bwd": (ctypes.c_int, [_c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                       ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "dwt_launch_count": (ctypes.c_int64, []),
     "dwt_profile_begin": (None, []),
     "dwt_profile_end": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

@@ -591,6 +591,46 @@ int dwt_augment_pair(const uint8_t* images, int64_t B, int src_h, int src_w, int
   return check_launch("augmentation kernel");
 }
 
+namespace {
+int pool_check(int64_t N, int64_t H, int64_t W, int64_t C, int k, int s, int p, int* OH, int* OW) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 4 != 0) return fail(DWT_E_INVALID, "bad pooling input [%lld,%lld,%lld,%lld] (C must be a multiple of 4)", (long long)N, (long long)H, (long long)W, (long long)C);
+  if (k < 1 || k > 15 || s < 1 || p < 0 || 2 * p > k) return fail(DWT_E_INVALID, "bad pooling window k=%d s=%d p=%d (k <= 15, pad <= k/2)", k, s, p);
+  if (H + 2 * p < k || W + 2 * p < k) return fail(DWT_E_INVALID, "pooling window larger than the padded image");
+  *OH = (int)((H + 2 * p - k) / s + 1);
+  *OW = (int)((W + 2 * p - k) / s + 1);
+  if (N * H * W * C >= ((int64_t)1 << 40)) return fail(DWT_E_UNSUPPORTED, "tensor too large");
+  return DWT_OK;
+}
+}  // namespace
+
+int dwt_maxpool_fwd(const float* x, float* y, uint8_t* argmax, int64_t N, int64_t H, int64_t W, int64_t C, int kernel,
+                    int stride, int padding, dwt_stream_t stream) {
+  int OH = 0, OW = 0;
+  if (int rc = pool_check(N, H, W, C, kernel, stride, padding, &OH, &OW)) return rc;
+  if (!x || !y || !argmax) return fail(DWT_E_INVALID, "null pointer argument");
+  if ((((uintptr_t)x | (uintptr_t)y) % 16) != 0 || (uintptr_t)argmax % 4 != 0) return fail(DWT_E_INVALID, "pooling tensors must be 16-byte aligned");
+  {
+    const double in = (double)N * H * W * C, out = (double)N * OH * OW * C;
+    Launch l("maxpool_fwd", nullptr, 4.0 * (in + out) + out, (cudaStream_t)stream);
+    dwt::maxpool_fwd_launch(x, y, argmax, (int)N, (int)H, (int)W, (int)C, OH, OW, kernel, stride, padding, (cudaStream_t)stream);
+  }
+  return check_launch("max-pool forward kernel");
+}
+
+int dwt_maxpool_bwd(const float* dy, const uint8_t* argmax, float* dx, int64_t N, int64_t H, int64_t W, int64_t C, int kernel,
+                    int stride, int padding, dwt_stream_t stream) {
+  int OH = 0, OW = 0;
+  if (int rc = pool_check(N, H, W, C, kernel, stride, padding, &OH, &OW)) return rc;
+  if (!dy || !dx || !argmax) return fail(DWT_E_INVALID, "null pointer argument");
+  if ((((uintptr_t)dy | (uintptr_t)dx) % 16) != 0 || (uintptr_t)argmax % 4 != 0) return fail(DWT_E_INVALID, "pooling tensors must be 16-byte aligned");
+  {
+    const double in = (double)N * H * W * C, out = (double)N * OH * OW * C;
+    Launch l("maxpool_bwd", nullptr, 4.0 * (in + out) + out, (cudaStream_t)stream);
+    dwt::maxpool_bwd_launch(dy, argmax, dx, (int)N, (int)H, (int)W, (int)C, OH, OW, kernel, stride, padding, (cudaStream_t)stream);
+  }
+  return check_launch("max-pool backward kernel");
+}
+
 int64_t dwt_launch_count(void) { return g_launches.load(); }
 
 void dwt_profile_begin(void) {

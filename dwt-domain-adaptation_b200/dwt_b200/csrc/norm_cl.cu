@@ -187,28 +187,42 @@ __device__ __forceinline__ int acc_index(int g, int a) {
   return (g / NSUB) * (NSUB * PER) + (g % NSUB) * PER + a;
 }
 
-// One thread per (group, domain): blockDim = (64 groups, D).  The dense algebra of the D domains runs in
-// parallel; the running-statistic EMA is then applied by the d == 0 thread of each group for d = 0..D-1 in
-// order from shared memory (any aliasing pattern, no atomics).
+// Finalize launches: kFinG groups per block, blockDim = (8 * kFinG, D).  EIGHT lanes serve one (group, domain): lane k
+// loads the group's accumulators of split row k (one batch of independent loads) and three xor-shuffles add the
+// rows in a fixed tree -- one thread per (group, domain) walking the S rows itself was a chain of ~30 dependent L2
+// round trips, 20 us per launch and 6 % of the ResNet-50-DWT step (profiles/ncu_r02_cl_site.md).  Lane 0 then
+// does the dense algebra in registers.  The running-statistic EMA follows the aliasing class found on the host:
+// all domains on ONE buffer pair (the shipped models) -> one closed-form read-modify-write
+// r' = k^D r + m sum_d k^(D-1-d) s_d; all distinct -> every domain's lane updates its own buffers; mixed -> the
+// d == 0 lane applies the domains in order.  No atomics.
+constexpr int kFinG = 32;
+
+template <int NACC>
+__device__ __forceinline__ void split_sum(const float* __restrict__ base, int S, int lane8, float (&a)[NACC]) {
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) a[i] = lane8 < S ? __ldcg(base + i) : 0.f;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+}
+
 template <int GS>
-__global__ void __launch_bounds__(256) cl_fwd_finalize_kernel(const float* __restrict__ red, int S, const float* __restrict__ shift,
-                                                              const Geom gm, const FwdFin fin) {
+__global__ void __launch_bounds__(8 * kFinG * DWT_MAX_DOMAINS) cl_fwd_finalize_kernel(const float* __restrict__ red, int S, const float* __restrict__ shift,
+                                                                                     const Geom gm, const FwdFin fin) {
   using SH = ClShape<GS>;
   constexpr int NST = GS + GS * GS;
-  __shared__ float sStat[DWT_MAX_DOMAINS][64][NST + 1];
-  __shared__ unsigned char sBad[DWT_MAX_DOMAINS][64];
-  const int gl = threadIdx.x, d = threadIdx.y, g = blockIdx.x * 64 + gl;
+  __shared__ float sStat[DWT_MAX_DOMAINS][kFinG][NST + 1];
+  __shared__ unsigned char sBad[DWT_MAX_DOMAINS][kFinG];
+  const int k8 = threadIdx.x & 7, gl = threadIdx.x >> 3, d = threadIdx.y, g = blockIdx.x * kFinG + gl;
   const int W = (gm.C >> 2) * SH::FWD;
   const float invM = 1.f / gm.M;
-  if (g < gm.G) {
-    float a[SH::FWD1];
-#pragma unroll
-    for (int i = 0; i < SH::FWD1; ++i) {
-      float s = 0.f;
-      for (int k = 0; k < S; ++k) s += red[((size_t)d * S + k) * W + acc_index<GS, SH::FWD1>(g, i)];
-      a[i] = s;
-    }
-    float mean[GS], cov[GS][GS];
+  const bool own = g < gm.G;
+  float a[SH::FWD1];
+  split_sum<SH::FWD1>(red + ((size_t)d * S + (k8 < S ? k8 : 0)) * W + acc_index<GS, SH::FWD1>(own ? g : 0, 0), S, k8, a);
+  float mean[GS], cov[GS][GS];
+  bool bad = false;
+  if (own && k8 == 0) {
 #pragma unroll
     for (int i = 0; i < GS; ++i) mean[i] = shift[(size_t)d * gm.C + g * GS + i] + a[i] * invM;
 #pragma unroll
@@ -218,7 +232,22 @@ __global__ void __launch_bounds__(256) cl_fwd_finalize_kernel(const float* __res
         const float c = a[GS + i * (i + 1) / 2 + j] * invM - (a[i] * invM) * (a[j] * invM);
         cov[i][j] = c; cov[j][i] = c;
       }
-    sBad[d][gl] = factor_thread<GS>(gm, fin, d, g, mean, cov, false) ? 1 : 0;
+    bad = factor_thread<GS>(gm, fin, d, g, mean, cov, false);
+  }
+  if (!fin.update_running) return;
+  if (gm.D == 1 || fin.aliased == 0) {            // this domain owns its buffers
+    if (own && k8 == 0 && !bad) {
+      float cf[GS * GS];
+#pragma unroll
+      for (int i = 0; i < GS; ++i)
+#pragma unroll
+        for (int j = 0; j < GS; ++j) cf[i * GS + j] = cov[i][j];
+      ema_direct<GS>(gm, fin, d, g, mean, cf);
+    }
+    return;
+  }
+  if (own && k8 == 0) {
+    sBad[d][gl] = bad ? 1 : 0;
 #pragma unroll
     for (int i = 0; i < GS; ++i) {
       sStat[d][gl][i] = mean[i];
@@ -227,9 +256,32 @@ __global__ void __launch_bounds__(256) cl_fwd_finalize_kernel(const float* __res
     }
   }
   __syncthreads();
-  if (fin.update_running && d == 0 && g < gm.G)
-    for (int dd = 0; dd < gm.D; ++dd)
-      if (!sBad[dd][gl]) ema_direct<GS>(gm, fin, dd, g, &sStat[dd][gl][0], &sStat[dd][gl][GS]);
+  if (!(own && k8 == 0 && d == 0)) return;
+  if (fin.aliased == 1) {
+    // one shared buffer pair: D sequential updates collapse to r' = k^n r + m sum_d k^(later good domains) s_d
+    const float m = fin.momentum, kk = 1.f - fin.momentum;
+    float* rc = fin.rcov[0] + (size_t)g * GS * GS;
+    float* rm = fin.rmean[0] + g * GS;
+    float c[GS * GS], u[GS];
+#pragma unroll
+    for (int e = 0; e < GS * GS; ++e) c[e] = rc[e];
+#pragma unroll
+    for (int e = 0; e < GS; ++e) u[e] = rm[e];
+    for (int dd = 0; dd < gm.D; ++dd) {
+      if (sBad[dd][gl]) continue;
+#pragma unroll
+      for (int e = 0; e < GS * GS; ++e) c[e] = m * (sStat[dd][gl][GS + e] * fin.unbias) + kk * c[e];
+#pragma unroll
+      for (int e = 0; e < GS; ++e) u[e] = m * sStat[dd][gl][e] + kk * u[e];
+    }
+#pragma unroll
+    for (int e = 0; e < GS * GS; ++e) rc[e] = c[e];
+#pragma unroll
+    for (int e = 0; e < GS; ++e) rm[e] = u[e];
+    return;
+  }
+  for (int dd = 0; dd < gm.D; ++dd)                 // mixed aliasing: plain ordered read-modify-write
+    if (!sBad[dd][gl]) ema_direct<GS>(gm, fin, dd, g, &sStat[dd][gl][0], &sStat[dd][gl][GS]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -384,26 +436,32 @@ __global__ void __launch_bounds__(kT, 2) cl_bwd_reduce_kernel(const float* __res
   }
 }
 
-// One thread per (group, domain), blockDim = (64, D); dgamma/dbeta are summed over the domains by the d == 0 thread
-// after the barrier.
+// Same thread arrangement as the forward finalize (8 lanes add the split rows of one (group, domain), lane 0 does the
+// algebra); dgamma / dbeta are summed over the domains by the d == 0 lane after the barrier.
 template <int GS>
-__global__ void __launch_bounds__(256) cl_bwd_finalize_kernel(const float* __restrict__ red, int S, const Geom gm, const BwdFin fin) {
+__global__ void __launch_bounds__(8 * kFinG * DWT_MAX_DOMAINS) cl_bwd_finalize_kernel(const float* __restrict__ red, int S, const Geom gm, const BwdFin fin) {
   using SH = ClShape<GS>;
-  const int gl = threadIdx.x, d = threadIdx.y, g = blockIdx.x * 64 + gl;
+  const int k8 = threadIdx.x & 7, gl = threadIdx.x >> 3, d = threadIdx.y, g = blockIdx.x * kFinG + gl;
   const int W = (gm.C >> 2) * SH::BWD;
-  if (g < gm.G) {
+  const bool own = g < gm.G;
+  float a[SH::BWD1];
+  if (red != nullptr) {
+    split_sum<SH::BWD1>(red + ((size_t)d * S + (k8 < S ? k8 : 0)) * W + acc_index<GS, SH::BWD1>(own ? g : 0, 0), S, k8, a);
+  } else {
+#pragma unroll
+    for (int i = 0; i < SH::BWD1; ++i) a[i] = 0.f;
+  }
+  if (own && k8 == 0) {
     float R[GS][GS], sdz[GS];
 #pragma unroll
     for (int i = 0; i < SH::BWD1; ++i) {
-      float s = 0.f;
-      if (red != nullptr)
-        for (int k = 0; k < S; ++k) s += red[((size_t)d * S + k) * W + acc_index<GS, SH::BWD1>(g, i)];
-      if (i < GS * GS) R[i / GS][i % GS] = s; else sdz[i - GS * GS] = s;
+      if (i < GS * GS) R[i / GS][i % GS] = a[i]; else sdz[i - GS * GS] = a[i];
     }
     bwd_finalize_thread<GS>(gm, fin, d, g, R, sdz, false);
   }
-  __syncthreads();
-  if ((fin.epi & DWT_EPI_AFFINE) && fin.dgamma != nullptr && d == 0 && g < gm.G) {
+  if (!((fin.epi & DWT_EPI_AFFINE) && fin.dgamma != nullptr)) return;
+  __syncthreads();                                  // the block's dgb_part writes (global) are visible block-wide
+  if (own && k8 == 0 && d == 0) {
 #pragma unroll
     for (int i = 0; i < GS; ++i) {
       float sg = 0.f, sb = 0.f;
@@ -551,7 +609,7 @@ void cl_vec_reduce(const float* partial, int nrows, int W, int D, int S, float* 
   vec_reduce_kernel<<<dim3((W + 63) / 64, D, S), 256, 0, st>>>(partial, nrows, W, out);
 }
 void cl_fwd_finalize(const float* red, int S, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st) {
-  CL_GS(gm.GS, (cl_fwd_finalize_kernel<kGS><<<(gm.G + 63) / 64, dim3(64, gm.D), 0, st>>>(red, S, shift, gm, fin)));
+  CL_GS(gm.GS, (cl_fwd_finalize_kernel<kGS><<<(gm.G + kFinG - 1) / kFinG, dim3(8 * kFinG, gm.D), 0, st>>>(red, S, shift, gm, fin)));
 }
 void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
               const float* gamma, const float* beta, const float* residual, uint8_t* mask, cudaStream_t st) {
@@ -566,7 +624,7 @@ void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas,
   CL_GS(gm.GS, CL_EPI_BWD(epi, (cl_bwd_reduce_kernel<kGS, kEPI><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, dout, gm, mean, w, gamma, beta, mask, partial))));
 }
 void cl_bwd_finalize(const float* red, int S, const Geom& gm, const BwdFin& fin, cudaStream_t st) {
-  CL_GS(gm.GS, (cl_bwd_finalize_kernel<kGS><<<(gm.G + 63) / 64, dim3(64, gm.D), 0, st>>>(red, S, gm, fin)));
+  CL_GS(gm.GS, (cl_bwd_finalize_kernel<kGS><<<(gm.G + kFinG - 1) / kFinG, dim3(8 * kFinG, gm.D), 0, st>>>(red, S, gm, fin)));
 }
 void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, int gz, int epi, const float* coef,
                   const float* mean, const float* w, const float* gamma, const float* beta, const uint8_t* mask, float* dres,

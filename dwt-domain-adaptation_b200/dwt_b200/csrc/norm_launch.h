@@ -79,6 +79,12 @@ void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, 
                   const float* mean, const float* w, const float* gamma, const float* beta, const uint8_t* mask, float* dres,
                   cudaStream_t st);
 
+// channels-last max-pool (pool.cu)
+void maxpool_fwd_launch(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C, int OH, int OW, int k, int s, int p,
+                        cudaStream_t st);
+void maxpool_bwd_launch(const float* dy, const uint8_t* idx, float* dx, int N, int H, int W, int C, int OH, int OW, int k, int s,
+                        int p, cudaStream_t st);
+
 // MEC loss (mec.cu)
 // paired target augmentation (augment.cu); mean / stdv are HOST arrays of 3
 void augment_pair_launch(const uint8_t* images, int B, int SH, int SW, int CR, const int* crop_plain, const int* crop_aug,

@@ -5,23 +5,36 @@
 //   bwd_reduce  R = sum_m dy (x-mean)^T
 //
 // 2*gs flop per 4 bytes read puts these above the FP32-core ridge but far below the TF32
-// tensor ridge: on tcgen05 they are HBM-bound.  Structure of one CTA
-// (320 threads, persistent over a contiguous range of [64 channels x 32 pixels] tiles):
+// tensor ridge: on tcgen05 they are HBM-bound.  Both kernels are persistent CTAs (two per
+// SM) over a contiguous range of [64 channels x 32 pixels] tiles, warp-specialised:
 //
 //   warp 0      TMA producer: cp.async.bulk.tensor.3d (box 32 px x 64 ch x 1 image, SWIZZLE_128B)
-//               into an 8-stage shared-memory ring, mbarrier complete_tx.
-//   warps 2-9   transform: in place, tile <- RN_tf32(tile - shift[channel]) (zero outside the
-//               tensor), row sums in registers, fence.proxy.async, arrive on the stage's "ready" barrier.
-//               Round-to-NEAREST operands make the TF32 product errors zero-mean, so they average
-//               out over the M ~ 1e5..1e6 samples instead of biasing the covariance (truncation would).
-//   warp 1      MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::tf32, M=64 N=64 K=8,
-//               both operands K-major straight from the swizzled tile (NCHW rows ARE K-major: the
-//               reference's transposing copy, whitening.py:46, disappears), fp32 accumulator in TMEM;
-//               tcgen05.commit releases the stage back to the producer.
-//   epilogue    tcgen05.ld the 64x64 accumulator (M=64 layout: row r -> lane 32*(r/16) + r%16),
-//               per-CTA partial -> global.  The fixed-order reduction of the partials and the dense
-//               algebra (Cholesky / inverse / EMA, or the backward coefficients) run as the small
-//               follow-up launches of norm_dense.cu.
+//               into a shared-memory ring, mbarrier complete_tx.
+//   warps 2-9   transform the landed tile for the tensor core (below), row sums in registers.
+//   warp 1      MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::tf32, fp32 accumulator in
+//               TMEM; tcgen05.commit releases the stage back to the producer.  Operands are K-major straight
+//               from the swizzled tile (NCHW rows ARE K-major: the reference's transposing copy,
+//               whitening.py:46, disappears).
+//   epilogue    tcgen05.ld the accumulator -> per-CTA partial -> global.  The fixed-order reduction of the
+//               partials and the dense algebra (Cholesky / inverse / EMA, or the backward coefficients) run
+//               as the small follow-up launches of norm_dense.cu.
+//
+// stats (tc_gram_kernel) -- SPLIT precision.  The covariance feeds a Cholesky factor whose error is the Gram
+// error times the condition number (the eps = 1e-3 shrinkage is absolute and stops helping once activations are
+// large), so a single tf32 pass is not enough (y errors of 1e-3..5e-3 at cond >= 1e4).  Each centred
+// sample s = x - K is split hi = trunc_tf32(s) (what the tensor core reads of an fp32 word anyway) and
+// lo = RN_tf32(s - hi), and
+//       G = HH + LH + LH^T         HH = sum hi hi^T,  LH = sum lo hi^T        (lo lo^T ~ 2^-20 G is dropped)
+// comes out of ONE M=128 N=80 K=8 MMA per 8 pixels: the A operand [hi ; lo] (128 rows: TMEM lanes 0..63 = hi of channels
+// 0..63, lanes 64..127 = their lo) is written to TENSOR MEMORY by the transform warps (tcgen05.st, lane = row; a warp
+// may only touch its own 32-lane quarter, so warps are hi warps or lo warps), the B operand is the hi tile written
+// back in place plus 16 constant rows (a row of ones: accumulator column 64 = the row sums the mean needs).
+// hi = RN_tf32(s), lo = s - hi.  Measured on B200 (tests/test_gpu_parity_r2.py): covariance error 6e-8 (single tf32
+// pass: 4e-6), y error at cond 1e3 / 1e4 3.6e-6 / 2.3e-5 (single pass 1.2e-4 / 2.9e-4, the fp32 reference itself
+// 3.2e-5 / 2.1e-4).
+//
+// bwd_reduce (tc_contract_kernel) -- single pass: R multiplies already-formed W's in the coefficient algebra and
+// its tf32 product errors are zero-mean over M >= 4096 samples (round-to-nearest operands).
 //
 // Reference: utils/whitening.py:46-47 (/root/reference) and its autograd transpose.
 #include <cuda.h>
@@ -43,6 +56,9 @@ constexpr int kTilePx = 32, kTileCh = 64;
 constexpr int kTileBytes = kTileCh * kTilePx * 4;       // 8192
 constexpr int kStagesStats = 12, kStagesBwd = 6;      // 97 KB per CTA, two CTAs per SM: ~190 KB of loads in flight per SM
 constexpr int kTmemCols = 64;
+// split-precision Gram kernel: accumulator (80 columns, padded to 96) + a ring of A-operand slots (32 columns =
+// 32 pixels each); two CTAs per SM share the 512 columns of tensor memory
+constexpr int kGramASlots = 5, kGramTmemCols = 256;
 
 // ------------------------------------------------------------------------------------------
 // shared memory carve-up
@@ -51,6 +67,7 @@ struct TcBarriers {
   uint64_t full[kStagesStats];
   uint64_t ready[kStagesStats];
   uint64_t empty[kStagesStats];
+  uint64_t a_empty[kGramASlots];     // Gram kernel: the MMAs that read tensor-memory A slot a have completed
   uint64_t accum;
   uint32_t tmem_slot;
   int flag;
@@ -242,6 +259,230 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------
+// split-precision Gram kernel (forward statistics): G = HH + LH + LH^T, see the file header
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// One lane's share of a landed tile: the 32 pixels of its channel row (8 swizzled 16-byte chunks; the 32 lanes of a
+// warp own 32 consecutive rows: four conflict-free wavefronts per access).  s = x - shift inside the tensor, 0 outside;
+// hi = RN_tf32(s) (an exact tf32 value: nothing depends on how the core would round), lo = s - hi (exact in fp32,
+// |lo| <= 2^-12 |s|; the core keeps its top 11 bits: a relative 2^-22 of s, sign-symmetric).
+//   LO = false (hi warps): hand hi to tensor memory AND write it back in place (the B operand);
+//   LO = true  (lo warps): hand lo to tensor memory.
+// Warps are homogeneous (no divergent halves): the tile is read from shared memory twice (the hi warp and the lo warp
+// of the same 32 rows meet at a named barrier between the reads and the write-back), but every ALU instruction
+// does useful work in all 32 lanes -- the interleaved hi/lo-in-one-warp variant read it once and was issue-bound
+// (1230 warp instructions per tile, 0.58 of the HBM peak; profiles/ncu_r02_tc_gram.md).
+template <bool LO>
+__device__ __forceinline__ void gram_transform_row(uint32_t tile, int row, float shift, int px0, int HW, bool rowok,
+                                                   uint32_t tmem_a, int pair_barrier) {
+  const uint32_t rbase = tile + 128u * (uint32_t)row;
+  const int sw = row & 7;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t4 = lds128(rbase + 16u * (uint32_t)(j ^ sw));
+    v[4 * j] = t4.x; v[4 * j + 1] = t4.y; v[4 * j + 2] = t4.z; v[4 * j + 3] = t4.w;
+  }
+  if (rowok && px0 + kTilePx <= HW) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] -= shift;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = (rowok && px0 + k < HW) ? v[k] - shift : 0.f;
+  }
+  // the hi warp overwrites the rows its partner lo warp reads: both have consumed their loads (the subtraction above)
+  // before either passes this 64-thread named barrier
+  asm volatile("bar.sync %0, 64;" ::"r"(pair_barrier) : "memory");
+  if constexpr (LO) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] -= round_tf32(v[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = round_tf32(v[k]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts128(rbase + 16u * (uint32_t)(j ^ sw), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  tmem_st32(tmem_a, v);
+}
+
+// Shared-memory stage of the Gram kernel: the landed [64 ch x 32 px] tile followed by 16 constant rows -- row 64 all
+// ones, rows 65..79 zero.  The MMA takes B = all 80 rows (N = 80), so accumulator column 64 collects sum_k A[:, k] * 1:
+// the per-channel sums of hi (hi rows) and lo (lo rows), i.e. the row sums the mean needs, for free on the tensor pipe.
+constexpr int kGramN = kTileCh + 16;
+constexpr int kGramStageBytes = kGramN * kTilePx * 4;            // 10240
+constexpr int kGramStages = 9;                                   // 90 KB + alignment: two CTAs per SM
+
+// ring position (stage or A slot) advanced by a fixed step without divisions
+struct RingPos {
+  int i, phase;
+  __device__ __forceinline__ RingPos(int start, int n) : i(start % n), phase((start / n) & 1) {}
+  __device__ __forceinline__ void advance(int step, int n) { i += step; if (i >= n) { i -= n; phase ^= 1; } }
+};
+
+__global__ void __launch_bounds__(kTcThreads, 2)
+tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restrict__ x, const Geom gm,
+               float* __restrict__ shift_out, float* __restrict__ partial) {
+  constexpr int STAGES = kGramStages, NA = kGramASlots;    // A slots behind the 96 accumulator columns: 96 + 5*32 = 256
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ TcBarriers bars;
+  __shared__ float sShift[kTileCh];
+  __shared__ float sRS[kTileCh];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int sb = blockIdx.y, d = blockIdx.z, ch0 = sb * kTileCh;
+  const TileRange tr(gm);
+  const int ntiles = tr.end - tr.begin;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.ready[s], 4); mbar_init(&bars.empty[s], 1); }
+    for (int a = 0; a < NA; ++a) mbar_init(&bars.a_empty[a], 1);
+    mbar_init(&bars.accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<kGramTmemCols>(&bars.tmem_slot);
+  if (tid >= 64 && tid < 128) {                    // pilot shift per channel (mean of <= 32 mid-image pixels of image 0)
+    const int r = tid - 64, c = ch0 + r;
+    float sh = 0.f;
+    if (c < gm.C) {
+      const int np = gm.HW < 32 ? gm.HW : 32, p0 = ((gm.HW - np) / 2) & ~3;
+      const float* px = x + ((size_t)d * gm.N * gm.C + c) * gm.HW + p0;
+      float a = 0.f;
+      for (int k = 0; k < np; ++k) a += __ldg(px + k);
+      sh = a / (float)np;
+    }
+    sShift[r] = sh;
+    if (blockIdx.x == 0) shift_out[((size_t)d * gridDim.y + sb) * kTileCh + r] = sh;
+  }
+  // constant rows 64..79 of every stage (128 16-byte chunks each): row 64 (chunks 0..7, un-swizzled: 64 & 7 == 0) = 1.0
+  for (int e = tid; e < STAGES * 128; e += kTcThreads) {
+    const int s = e >> 7, q = e & 127;
+    const float val = q < 8 ? 1.f : 0.f;
+    sts128(smem_u32(smem + (size_t)s * kGramStageBytes + kTileBytes) + 16u * (uint32_t)q, val, val, val, val);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_slot;
+  const uint32_t tmem_d = tmem, tmem_a0 = tmem + 96;            // accumulator: columns 0..79; A slots from column 96
+
+  // transform-warp geometry: two sets of four warps take alternate tiles; a warp may only touch the TMEM quarter
+  // warp & 3: quarters 0, 1 = hi rows of channels 0..63 (lane = channel), quarters 2, 3 = their lo rows
+  const int quad = warp & 3, set = (warp - 2) >> 2;
+  const bool lo_warp = quad >= 2;
+  const int row = 32 * (quad & 1) + lane;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      RingPos st(0, STAGES);
+      int n = tr.begin / tr.PB, pb = tr.begin - n * tr.PB;
+      for (int it = 0; it < ntiles; ++it) {
+        mbar_wait(&bars.empty[st.i], st.phase ^ 1);
+        mbar_arrive_expect_tx(&bars.full[st.i], kTileBytes);
+        tma_load_3d(smem + (size_t)st.i * kGramStageBytes, &map_x, pb * kTilePx, ch0, d * gm.N + n, &bars.full[st.i]);
+        st.advance(1, STAGES);
+        if (++pb == tr.PB) { pb = 0; ++n; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: D[128 x 80] += [hi ; lo] (tensor memory) x [hi tile ; ones ; 0]^T (shared memory) =====
+    constexpr uint32_t idesc = make_idesc_tf32(128, kGramN);
+    RingPos st(0, STAGES), as(0, NA);
+    for (int it = 0; it < ntiles; ++it) {
+      mbar_wait(&bars.ready[st.i], st.phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + (size_t)st.i * kGramStageBytes));
+#pragma unroll
+        for (int k = 0; k < kTilePx / 8; ++k)
+          umma_tf32_ts(tmem_d, tmem_a0 + (uint32_t)(as.i * kTilePx + 8 * k), bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&bars.empty[st.i]);
+        umma_commit(&bars.a_empty[as.i]);
+        if (it == ntiles - 1) umma_commit(&bars.accum);
+      }
+      __syncwarp();
+      st.advance(1, STAGES); as.advance(1, NA);
+    }
+  } else {
+    // ===== transform warps =====
+    const float shift = sShift[row];
+    const bool rowok = (ch0 + row) < gm.C;
+    const uint32_t smem0 = smem_u32(smem), ta0 = tmem_a0 + ((uint32_t)(quad * 32) << 16);
+    RingPos st(set, STAGES), as(set, NA);
+    const int pair_bar = 1 + 2 * set + (quad & 1);       // hi warp (quarter q) and lo warp (quarter q + 2) of the same rows
+    const int t0 = tr.begin + set;
+    int n = t0 / tr.PB, pb = t0 - n * tr.PB;
+    for (int it = set; it < ntiles; it += 2) {
+      mbar_wait(&bars.full[st.i], st.phase);
+      mbar_wait(&bars.a_empty[as.i], as.phase ^ 1);
+      tc_fence_after();
+      const uint32_t tile = smem0 + (uint32_t)(st.i * kGramStageBytes), ta = ta0 + (uint32_t)(as.i * kTilePx);
+      if (lo_warp) gram_transform_row<true>(tile, row, shift, pb * kTilePx, gm.HW, rowok, ta, pair_bar);
+      else gram_transform_row<false>(tile, row, shift, pb * kTilePx, gm.HW, rowok, ta, pair_bar);
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.ready[st.i]);
+      st.advance(2, STAGES); as.advance(2, NA);
+      pb += 2;
+      while (pb >= tr.PB) { pb -= tr.PB; ++n; }
+    }
+  }
+
+  // ===== epilogue: G = HH + LH + LH^T and the row sums -> this CTA's partial row =====
+  const int nacc = kTileCh * kTileCh + kTileCh;
+  float* prow = partial + (((size_t)d * gridDim.y + sb) * gridDim.x + blockIdx.x) * nacc;
+  float* sT = reinterpret_cast<float*>(smem);      // LH, [64][65]; the tile ring is drained by now
+  float P[kTileCh], rs = 0.f;
+  const bool epi_warp = warp >= 2 && warp < 6;     // one warp per TMEM quarter
+  if (epi_warp && ntiles > 0) {
+    mbar_wait(&bars.accum, 0);
+    tc_fence_after();
+    float tail[16];
+    tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16), reinterpret_cast<float(&)[32]>(P[0]));
+    tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + 32, reinterpret_cast<float(&)[32]>(P[32]));
+    tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + 64, tail);
+    tc_fence_before();
+    rs = tail[0];                                  // sum over the CTA's samples of hi (hi rows) / lo (lo rows)
+    if (lo_warp) {
+#pragma unroll
+      for (int j = 0; j < kTileCh; ++j) sT[row * (kTileCh + 1) + j] = P[j];          // LH[row][j]
+      sRS[row] = rs;
+    }
+  }
+  __syncthreads();
+  if (epi_warp && !lo_warp) {
+    if (ntiles > 0) {
+#pragma unroll
+      for (int j4 = 0; j4 < kTileCh / 4; ++j4) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = 4 * j4 + k;
+          o[k] = (P[j] + sT[row * (kTileCh + 1) + j]) + sT[j * (kTileCh + 1) + row];   // HH + LH + LH^T
+        }
+        *reinterpret_cast<float4*>(prow + row * kTileCh + 4 * j4) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      prow[kTileCh * kTileCh + row] = rs + sRS[row];
+    } else {
+      for (int j = 0; j < kTileCh; ++j) prow[row * kTileCh + j] = 0.f;
+      prow[kTileCh * kTileCh + row] = 0.f;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<kGramTmemCols>(tmem); }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -259,7 +500,7 @@ int make_map(CUtensorMap* map, const float* base, const Geom& gm) {
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-size_t tc_smem_bytes(bool two) { return (size_t)(two ? kStagesBwd * 2 : kStagesStats) * kTileBytes + 1024; }
+size_t tc_smem_bytes(bool two) { return two ? (size_t)kStagesBwd * 2 * kTileBytes + 1024 : (size_t)kGramStages * kGramStageBytes + 1024; }
 
 }  // namespace
 
@@ -269,11 +510,11 @@ int tc_init() {
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
   if (e != cudaSuccess || fn == nullptr || q != cudaDriverEntryPointSuccess) return e == cudaSuccess ? -1 : (int)e;
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  e = cudaFuncSetAttribute(tc_contract_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(false));
+  e = cudaFuncSetAttribute(tc_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(false));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(tc_contract_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(true));
   // two ~97 KB CTAs per SM need the full shared-memory carve-out
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_contract_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gram_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_contract_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e == cudaSuccess) e = (cudaError_t)dense_init();
   if (e == cudaSuccess) return tc_apply_init();
@@ -296,7 +537,7 @@ int tc_stats(const float* x, const Geom& gm, int nchunks, float* shift, float* p
   bind_context();
   if (int rc = make_map(&mx, x, gm)) return rc;
   dim3 grid(nchunks, tc_superblocks(gm), gm.D);
-  tc_contract_kernel<false><<<grid, kTcThreads, tc_smem_bytes(false), st>>>(mx, mx, x, gm, nullptr, shift, partial);
+  tc_gram_kernel<<<grid, kTcThreads, tc_smem_bytes(false), st>>>(mx, x, gm, shift, partial);
   return 0;
 }
 

@@ -33,6 +33,7 @@ EXPANSION = 4
 
 
 _REPLICATED = [False]          # set by collect_stats(): one copy of the batch stands for all three branches
+_BATCHED_COUNTERS = [False]    # set inside ResNet50DWT.forward (fused sites): the model has bumped every BN step counter itself
 
 
 class WhitenScaleShift(nn.Module):
@@ -99,13 +100,14 @@ class _SiteOwner(nn.Module):
             if fused is not None:
                 mods = [getattr(self, n) for n in names]
                 return fused(x, [m.wh if whiten else m for m in mods], gamma, beta, True, residual=residual,
-                             replicated=_REPLICATED[0])
+                             replicated=_REPLICATED[0], count_batches=not _BATCHED_COUNTERS[0])
             return torch.relu_(self._site(tag, x, relu=False) + residual)
         if self.training:
             fused = getattr(self, f"_fused_{tag}", None)
             mods = [getattr(self, n) for n in names]
             if fused is not None:
-                return fused(x, [m.wh if whiten else m for m in mods], gamma, beta, relu, replicated=_REPLICATED[0])
+                return fused(x, [m.wh if whiten else m for m in mods], gamma, beta, relu, replicated=_REPLICATED[0],
+                             count_batches=not _BATCHED_COUNTERS[0])
             if _REPLICATED[0]:
                 raise RuntimeError("replicated statistics collection needs site_mode='fused'")
             parts = torch.split(x, x.shape[0] // 3, dim=0)
@@ -141,15 +143,20 @@ class Bottleneck(_SiteOwner):
 
 
 class ResNet50DWT(_SiteOwner):
-    def __init__(self, layers, state_dict, num_classes=65, group_size=4, site_mode="modules"):
+    def __init__(self, layers, state_dict, num_classes=65, group_size=4, site_mode="modules", stem_pad=0):
         super().__init__()
+        # stem_pad = 4 / 8: feed the 7x7 stem convolution a zero-padded 4- / 8-channel image and the equally padded
+        # weight -- identical arithmetic (the extra products are exact zeros), but cuDNN has no tensor-core kernel for
+        # a 3-channel NHWC tensor and falls back to a legacy engine (2.0 ms forward + 2.2 ms weight gradient per
+        # step on B200, profiles/launches_r02_step.md).  The parameter keeps the reference's [64, 3, 7, 7] shape.
+        self.stem_pad = stem_pad
         if site_mode not in ("modules", "fused"):
             raise ValueError("site_mode must be 'modules' or 'fused'")
         stats = {k: v for k, v in state_dict.items() if "bn" in k or "downsample" in k}
         self.site_mode = site_mode
         self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
         self._add_site(layers, "1", "bn1", 64, True, group_size, stats, site_mode)
-        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)       # resnet50_dwt_mec_officehome.py:295
         inplanes = 64
         for li, (planes, blocks, stride) in enumerate(_STAGES, start=1):
             seq = []
@@ -168,19 +175,52 @@ class ResNet50DWT(_SiteOwner):
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
+    def _stem(self, x):
+        if not self.stem_pad or x.shape[1] >= self.stem_pad:
+            return self.conv1(x)
+        extra = self.stem_pad - x.shape[1]
+        fmt = torch.channels_last if (x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()) \
+            else torch.contiguous_format
+        xp = torch.zeros((x.shape[0], self.stem_pad) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device).contiguous(memory_format=fmt)
+        xp[:, :x.shape[1]] = x
+        w = torch.nn.functional.pad(self.conv1.weight, (0, 0, 0, 0, 0, extra))
+        if fmt == torch.channels_last:
+            w = w.contiguous(memory_format=torch.channels_last)
+        c = self.conv1
+        return torch.nn.functional.conv2d(xp, w, None, c.stride, c.padding, c.dilation, c.groups)
+
+    def _bump_counters(self):
+        """All 126 `num_batches_tracked += 1` (batch_norm.py:58) of a fused-site training forward as one launch."""
+        cs = getattr(self, "_bn_counters", None)
+        if cs is None:
+            cs = [m.num_batches_tracked for m in self.modules()
+                  if hasattr(m, "num_batches_tracked") and m.num_batches_tracked is not None and getattr(m, "track_running_stats", False)]
+            object.__setattr__(self, "_bn_counters", cs)
+        if cs:
+            torch._foreach_add_(cs, 1)
+
     def forward(self, x):
-        x = self.maxpool(self._site("1", self.conv1(x), relu=True))
-        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        batched = self.training and self.site_mode == "fused"
+        if batched:
+            self._bump_counters()
+        _BATCHED_COUNTERS[0] = batched
+        try:
+            x = self.maxpool(self._site("1", self._stem(x), relu=True))
+            x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        finally:
+            _BATCHED_COUNTERS[0] = False
         return self.fc_out(torch.flatten(self.avgpool(x), 1))
 
 
-def build_resnet50_dwt(state_dict, layers, site_mode="modules", num_classes=65, channels_last=False):
+def build_resnet50_dwt(state_dict, layers, site_mode="modules", num_classes=65, channels_last=False, stem_pad=0):
     """state_dict uses the reference checkpoint's key names *without* the 7-char
     ``module.`` prefix (resnet50_dwt_mec_officehome.py:370-376).  channels_last=True converts the
     convolution weights to torch.channels_last so that, fed channels-last images, every activation
     stays NHWC (no cuDNN NCHW<->NHWC copies); results are identical, only strides change."""
-    model = ResNet50DWT(layers, state_dict, num_classes=num_classes, site_mode=site_mode)
+    model = ResNet50DWT(layers, state_dict, num_classes=num_classes, site_mode=site_mode, stem_pad=stem_pad)
     model.load_state_dict(state_dict, strict=False)
+    if channels_last and hasattr(layers, "MaxPool2d"):
+        model.maxpool = layers.MaxPool2d(3, stride=2, padding=1)    # the library's channels-last kernel pair (no state)
     if channels_last:
         # only the convolution weights: Module.to(memory_format=...) would also re-stride the [1,C,1,1]
         # running-mean buffers into fresh tensors and silently break the aliasing of the three domain branches

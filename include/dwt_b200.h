@@ -22,6 +22,7 @@
  *   dwt_head_loss_fwd_bwd  the training loop's NLL + lambda*MEC   resnet50_dwt_mec_officehome.py:421-428
  *   dwt_augment_pair the loader's two target views  resnet50_dwt_mec_officehome.py:481-492,526-542;
  *                                                   utils/folder.py:127-147
+ *   dwt_maxpool_fwd/bwd  nn.MaxPool2d(3, 2, 1) behind the stem site   resnet50_dwt_mec_officehome.py:295,337-338
  *
  * Threading: calls may come from any host thread (PyTorch runs backward on its own); the error text is
  * per thread.  One process drives ONE device (the reference's and torchrun's model): kernel attributes
@@ -187,6 +188,19 @@ DWT_API int dwt_head_loss_fwd_bwd(const float *logits, const int64_t *labels, in
 DWT_API int dwt_augment_pair(const uint8_t *images, int64_t B, int src_h, int src_w, int crop, const int32_t *crop_plain,
                      const int32_t *crop_aug, const uint8_t *flip, const float *affine, const float *mean,
                      const float *stdv, float *out_plain, float *out_aug, int layout, dwt_stream_t stream);
+
+/*
+ * Channels-last max-pool and its backward: the op between the stem whitening site and layer1
+ * (nn.MaxPool2d(3, 2, 1), resnet50_dwt_mec_officehome.py:295,337-338).  Semantics = torch max_pool2d (dilation 1,
+ * ceil_mode False) and its autograd, bit for bit including ties (first maximum in row-major window order) and NaN.
+ *   x  [N, H, W, C] fp32 (torch.channels_last), C % 4 == 0;  y [N, OH, OW, C], OH = (H + 2*padding - kernel)/stride + 1
+ *   argmax [N, OH, OW, C] uint8: window-local index kh*kernel + kw of the maximum (written by fwd, read by bwd)
+ *   dy [N, OH, OW, C] -> dx [N, H, W, C] (every element written; no atomics, deterministic)
+ */
+DWT_API int dwt_maxpool_fwd(const float *x, float *y, uint8_t *argmax, int64_t N, int64_t H, int64_t W, int64_t C,
+                    int kernel, int stride, int padding, dwt_stream_t stream);
+DWT_API int dwt_maxpool_bwd(const float *dy, const uint8_t *argmax, float *dx, int64_t N, int64_t H, int64_t W, int64_t C,
+                    int kernel, int stride, int padding, dwt_stream_t stream);
 
 /*
  * Measurement hooks (used by bench.py; not part of the reference's surface).

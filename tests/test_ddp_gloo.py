@@ -3,7 +3,8 @@
 The product layers have no CPU path, so the harness model is built on the CPU port of the
 reference layers (oracle/torch_port.py) -- what is under test is the host-side plumbing of
 bench.py (FlatGradAllReduce + train_step): one process per rank, rank-local whitening statistics
-(never exchanged), gradients averaged by one flat all-reduce, SURVEY.md §8e.
+(never exchanged), gradients averaged through the flat buffer in three segments that are all-reduced
+as backward completes them (post-accumulate hooks, async collectives joined in reduce()), SURVEY.md §8e.
 """
 import os
 import socket

@@ -215,7 +215,9 @@ def test_mec_vs_oracle_batch64(dev):
 
 # --------------------------------------------------------------------------- fused domain triple
 @pytest.mark.parametrize("kind,c,hw,gs", [("whiten", 64, 28, 4), ("whiten", 256, 14, 4), ("bn", 128, 14, 1),
-                                           ("bn", 512, 7, 1), ("whiten", 16, 9, 2)])
+                                           ("bn", 512, 7, 1), ("whiten", 16, 9, 2),
+                                           ("whiten", 64, 12, 8),       # large groups, tiled kernels (M < 4096)
+                                           ("whiten", 128, 32, 64)])    # large groups, TMA + tcgen05 kernels, D = 3
 @pytest.mark.parametrize("relu", [True, False])
 def test_fused_triple_vs_oracle(kind, c, hw, gs, relu, dev):
     """DomainTripleNorm == split/3 -> 3 modules on ALIASED buffers -> cat -> *gamma+beta -> relu

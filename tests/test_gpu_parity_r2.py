@@ -343,3 +343,27 @@ def test_pointer_arguments_are_validated(dev):
     ver = v0._version
     bn(x)
     assert v0._version > ver                                                  # the in-place EMA is visible to autograd
+
+
+# --------------------------------------------------------------------------- channels-last max-pool (stem tail)
+@pytest.mark.parametrize("shape,k,s,p", [((6, 64, 112, 112), 3, 2, 1), ((3, 8, 9, 7), 3, 2, 1), ((2, 16, 8, 8), 2, 2, 0),
+                                          ((2, 4, 5, 6), 3, 1, 1), ((1, 12, 7, 7), 5, 3, 2)])
+def test_maxpool_is_bit_exact_vs_torch(shape, k, s, p, dev):
+    """dwt_b200.MaxPool2d == F.max_pool2d forward AND backward, bit for bit: post-ReLU inputs are full of ties (windows
+    of zeros), and the gradient must go to the same element (first maximum in row-major window order)."""
+    import torch.nn.functional as Fn
+    import dwt_b200
+    torch.manual_seed(sum(shape) + k)
+    x = torch.relu(torch.randn(*shape, device=dev)).contiguous(memory_format=torch.channels_last)   # ~50 % exact zeros
+    x[0, 0, 0, 0] = float("nan")
+    g = torch.randn(shape[0], shape[1], (shape[2] + 2 * p - k) // s + 1, (shape[3] + 2 * p - k) // s + 1, device=dev)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = dwt_b200.MaxPool2d(k, s, p)(xa)
+    yb = Fn.max_pool2d(xb, k, s, p)
+    assert ya.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(torch.nan_to_num(ya, nan=-7.0), torch.nan_to_num(yb, nan=-7.0))
+    ya.backward(g); yb.backward(g)
+    assert torch.equal(xa.grad, xb.grad)
+    from dwt_b200 import _native
+    with pytest.raises(_native.NativeError, match="channels_last"):
+        dwt_b200.MaxPool2d(k, s, p)(x.contiguous())

@@ -1,10 +1,17 @@
-"""CPU emulation of the single-pass TF32 Gram contraction (csrc/norm_tc.cu): covariance error vs sample count.
+"""CPU emulation of the tf32 Gram contraction of the forward statistics (csrc/norm_tc.cu): covariance and y error of
 
-  G = sum_m RN_tf32(x_m - K) RN_tf32(x_m - K)^T   (products exact, fp32 accumulation emulated in fp64: the kernel
-  keeps per-CTA partials of <= a few thousand samples each and reduces them in fixed order)
-compared with the fp64 covariance; also the same with TRUNCATED operands (what feeding the raw tile would do) and the
-resulting error of y = W (x - mu).  Pure numpy.      python tools/tf32_gram_accuracy.py
+  single   G = sum RN_tf32(s) RN_tf32(s)^T                        (round-1 kernel: one tf32 pass)
+  split    G = HH + LH + LH^T,  hi = trunc_tf32(s), lo = RN_tf32(s - hi)   (round-2 tc_gram_kernel)
+  fp32     the same sums with fp32 operands                        (what the reference's torch.bmm computes)
+
+against the fp64 covariance, over condition number, activation scale and |mean|/sigma.  s = x - K with the pilot
+shift K; products are exact in fp32 and the accumulation is emulated in fp64 (the kernel keeps per-CTA partials of a
+few thousand samples and reduces them in fixed order); optionally with a truncating fp32 accumulator per 8-sample
+MMA step (--rz) as a pessimistic model of the tensor core's accumulate.  Pure numpy.
+      python tools/tf32_gram_accuracy.py [--rz]
 """
+import sys
+
 import numpy as np
 
 
@@ -17,31 +24,50 @@ def tr(a):
     return (a.astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64)
 
 
-def run(M, gs=64, cond=1e2, offset=2.0, seed=0):
+def acc(a, b, rz, chunk=2048):
+    """sum_m a[:, m] b[:, m]^T; rz: per-CTA chunks accumulated 8 samples at a time into a TRUNCATED fp32 accumulator."""
+    if not rz:
+        return a @ b.T
+    tot = np.zeros((a.shape[0], b.shape[0]))
+    for c0 in range(0, a.shape[1], chunk):
+        d = np.zeros((a.shape[0], b.shape[0]), np.float32)
+        for k in range(c0, min(c0 + chunk, a.shape[1]), 8):
+            t = d.astype(np.float64) + a[:, k:k + 8] @ b[:, k:k + 8].T
+            t32 = t.astype(np.float32)
+            over = np.abs(t32.astype(np.float64)) > np.abs(t)          # RN went away from zero: step back one ulp
+            d = np.where(over, np.nextafter(t32, np.float32(0)), t32)
+        tot += d.astype(np.float64)
+    return tot
+
+
+def run(M, gs=64, cond=1e2, scale=1.0, mos=2.0, seed=0, rz=False):
     rng = np.random.default_rng(seed)
     q, _ = np.linalg.qr(rng.standard_normal((gs, gs)))
-    x = (q * np.sqrt(np.logspace(0, -np.log10(cond), gs))) @ rng.standard_normal((gs, M)) + offset
+    x = (q * (scale * np.sqrt(np.logspace(0, -np.log10(cond), gs)))) @ rng.standard_normal((gs, M))
+    x = x + mos * x.std(1, keepdims=True)
     K = x[:, M // 2 - 16:M // 2 + 16].mean(1, keepdims=True) if M >= 32 else x.mean(1, keepdims=True)   # pilot shift
     xs = (x.astype(np.float32) - K.astype(np.float32)).astype(np.float32).astype(np.float64)
     s1 = xs.sum(1, keepdims=True) / M
-
-    def cov_from(op):
-        o = op(xs)
-        return o @ o.T / M - s1 @ s1.T
-
     exact = np.cov(x, bias=True)
     w = lambda c: np.linalg.inv(np.linalg.cholesky((1 - 1e-3) * c + 1e-3 * np.eye(gs)))       # noqa: E731
-    y64 = w(exact) @ (x - x.mean(1, keepdims=True))
-    out = []
-    for op in (rn, tr):
-        c = cov_from(op)
-        out.append(np.linalg.norm(c - exact) / np.linalg.norm(exact))
-        out.append(np.linalg.norm(w(c) @ (x - x.mean(1, keepdims=True)) - y64) / np.linalg.norm(y64))
+    xc = x - x.mean(1, keepdims=True)
+    y64 = w(exact) @ xc
+    hi = tr(xs)
+    lo = rn(xs - hi)
+    lh = acc(lo, hi, rz)
+    grams = {"single": acc(rn(xs), rn(xs), rz), "split": acc(hi, hi, rz) + lh + lh.T, "fp32": acc(xs, xs, False)}
+    out = {}
+    for name, g in grams.items():
+        c = g / M - s1 @ s1.T
+        out[name] = (np.linalg.norm(c - exact) / np.linalg.norm(exact), np.linalg.norm(w(c) @ xc - y64) / np.linalg.norm(y64))
     return out
 
 
 if __name__ == "__main__":
-    print(f"{'M':>8} | {'cov err RN':>11} {'y err RN':>11} | {'cov err trunc':>13} {'y err trunc':>11}")
-    for M in (144, 1024, 4096, 65536, 802816 // 8):
-        r = run(M)
-        print(f"{M:8d} | {r[0]:11.2e} {r[1]:11.2e} | {r[2]:13.2e} {r[3]:11.2e}")
+    rz = "--rz" in sys.argv
+    M = 4704 if rz else 65536
+    print(f"M = {M}, gs = 64, eps = 1e-3" + (", truncating fp32 accumulator per 8-sample step" if rz else ""))
+    print(f"{'cond':>6} {'scale':>6} {'|mu|/sd':>8} | " + " | ".join(f"{n + ' cov':>11} {n + ' y':>10}" for n in ("single", "split", "fp32")))
+    for cond, scale, mos in [(1e2, 1, 2), (1e3, 10, 0), (1e4, 30, 0), (1e4, 100, 0), (1e1, 1, 50), (1e3, 10, 50)]:
+        r = run(M, cond=cond, scale=scale, mos=mos, rz=rz)
+        print(f"{cond:6.0e} {scale:6.0f} {mos:8.0f} | " + " | ".join(f"{r[n][0]:11.2e} {r[n][1]:10.2e}" for n in ("single", "split", "fp32")))
