@@ -793,7 +793,7 @@ def main():
     ap.add_argument("--sites-out", default="", help="write the per-site kernel table (JSON) here")
     ap.add_argument("--stem-pad", type=int, default=0, choices=[0, 4, 8],
                     help="zero-pad the 3-channel image (and the stem weight) to this many channels for cuDNN")
-    ap.add_argument("--grad-segments", type=int, default=3, choices=[1, 2, 3],
+    ap.add_argument("--grad-segments", type=int, default=1, choices=[1, 2, 3],
                     help="pieces the flat gradient buffer is all-reduced in (1 = one collective after backward)")
     ap.add_argument("--micro-n", type=int, default=256)
     ap.add_argument("--micro-gs", type=int, default=64)
