@@ -347,8 +347,7 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
       }
       if (int rc = check_launch("channels-last statistics kernel")) return rc;
       Launch l("cl_fwd_finalize", &p.gm, 0.0, st);
-      dwt::cl_vec_reduce(w.partial, cp.nred, dwt::cl_fwd_width((int)C, GS), D, cp.S, w.red, st);
-      dwt::cl_fwd_finalize(w.red, cp.S, w.shift, p.gm, fin, st);
+      dwt::cl_fwd_finalize(w.partial, cp.nred, w.shift, p.gm, fin, st);
     } else {
       Launch l("eval_prep", &p.gm, 0.0, st);
       dwt::small_eval_prep(p.gm, fin, st);
@@ -444,8 +443,7 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
       }
       if (int rc = check_launch("channels-last backward reduction kernel")) return rc;
       Launch l("cl_bwd_finalize", &p.gm, 0.0, st);
-      dwt::cl_vec_reduce(w.partial, cp.nred, dwt::cl_bwd_width((int)C, GS), D, cp.S, w.red, st);
-      dwt::cl_bwd_finalize(w.red, cp.S, p.gm, fin, st);
+      dwt::cl_bwd_finalize(w.partial, cp.nred, p.gm, fin, st);
     } else {
       Launch l("bwd_prep", &p.gm, 0.0, st);
       dwt::small_bwd_prep(p.gm, fin, st);

@@ -10,12 +10,12 @@
 // COLUMN q (channels 4q..4q+3) and walks down the rows (pixels); a warp therefore reads 512
 // contiguous bytes per step, and a thread's accumulators always belong to the same channels.
 // A CTA covers CW = min(C/4, 256) columns x a contiguous range of rows; 256/CW threads share a column
-// and are summed in shared memory.  Per-CTA partial moments go to global memory, a small
-// many-CTA kernel adds them in fixed order, and a one-thread-per-group kernel does the dense algebra
-// (small_algebra.cuh) for all domains in order -- so the running-statistic EMA needs no atomics.
+// and are summed in shared memory.  Per-CTA partial moments go to global memory; one small finalize launch
+// (a warp per float4 column and domain) adds them in fixed order and does the dense algebra
+// (small_algebra.cuh) and the ordered running-statistic EMA -- no atomics.
 //
-//   cl_stats -> vec_reduce -> cl_fwd_finalize -> cl_apply          (forward, 12 B/element)
-//   cl_bwd_reduce -> vec_reduce -> cl_bwd_finalize -> cl_bwd_apply (backward, 20 B/element)
+//   cl_stats -> cl_fwd_finalize -> cl_apply          (forward, 12 B/element)
+//   cl_bwd_reduce -> cl_bwd_finalize -> cl_bwd_apply (backward, 20 B/element)
 //
 // Sweep order (round 2).  The tensor a pass reads was touched a moment ago: x was just WRITTEN front to back
 // by the producing convolution, and the second pass of a site re-reads what the first pass just read.  126 MB
@@ -155,31 +155,6 @@ __global__ void __launch_bounds__(kT, 3) cl_stats_kernel(const float* __restrict
   }
 }
 
-// out[d][s][e] = sum over the rows of split s of partial[d][row][e]  (fixed order).
-// grid (ceil(W/64), D, S), 256 threads = 4 row-quarters x 64 elements.
-__global__ void __launch_bounds__(256) vec_reduce_kernel(const float* __restrict__ partial, int nrows, int W,
-                                                         float* __restrict__ out) {
-  __shared__ float sQ[4][64];
-  const int l = threadIdx.x & 63, qt = threadIdx.x >> 6, S = gridDim.z;
-  const int e = blockIdx.x * 64 + l, d = blockIdx.y, s = blockIdx.z;
-  const int a0 = (int)((long long)nrows * s / S), a1 = (int)((long long)nrows * (s + 1) / S);
-  const int c0 = a0 + ((a1 - a0) * qt) / 4, c1 = a0 + ((a1 - a0) * (qt + 1)) / 4;
-  const float* base = partial + (size_t)d * nrows * W;
-  float acc = 0.f;
-  if (e < W) {
-    int c = c0;
-    for (; c + 4 <= c1; c += 4) {
-      const float v0 = __ldcg(base + (size_t)(c + 0) * W + e), v1 = __ldcg(base + (size_t)(c + 1) * W + e);
-      const float v2 = __ldcg(base + (size_t)(c + 2) * W + e), v3 = __ldcg(base + (size_t)(c + 3) * W + e);
-      acc = (((acc + v0) + v1) + v2) + v3;
-    }
-    for (; c < c1; ++c) acc += __ldcg(base + (size_t)c * W + e);
-  }
-  sQ[qt][l] = acc;
-  __syncthreads();
-  if (qt == 0 && e < W) out[((size_t)d * S + s) * W + e] = ((sQ[0][l] + sQ[1][l]) + sQ[2][l]) + sQ[3][l];
-}
-
 // index of accumulator a of group g inside a W-vector
 template <int GS, int PER>
 __device__ __forceinline__ int acc_index(int g, int a) {
@@ -187,101 +162,122 @@ __device__ __forceinline__ int acc_index(int g, int a) {
   return (g / NSUB) * (NSUB * PER) + (g % NSUB) * PER + a;
 }
 
-// Finalize launches: kFinG groups per block, blockDim = (8 * kFinG, D).  EIGHT lanes serve one (group, domain): lane k
-// loads the group's accumulators of split row k (one batch of independent loads) and three xor-shuffles add the
-// rows in a fixed tree -- one thread per (group, domain) walking the S rows itself was a chain of ~30 dependent L2
-// round trips, 20 us per launch and 6 % of the ResNet-50-DWT step (profiles/ncu_r02_cl_site.md).  Lane 0 then
-// does the dense algebra in registers.  The running-statistic EMA follows the aliasing class found on the host:
-// all domains on ONE buffer pair (the shipped models) -> one closed-form read-modify-write
-// r' = k^D r + m sum_d k^(D-1-d) s_d; all distinct -> every domain's lane updates its own buffers; mixed -> the
-// d == 0 lane applies the domains in order.  No atomics.
-constexpr int kFinG = 32;
+// Finalize launches (one per pass, between the reduction and the elementwise kernel).  blockDim = (32, kFinQ columns,
+// D domains): ONE WARP serves one (float4 column, domain).  Lane l adds the per-CTA partial rows l, l+32, ... of its
+// column in ascending order (independent 8-byte loads, several rows in flight), five xor-shuffles add the lanes in a
+// fixed tree, and lane 0 does the dense algebra of the column's 4/gs groups in registers.  This replaced a many-CTA
+// `vec_reduce` launch plus a finalize launch in which one thread per (group, domain) walked the reduced rows itself --
+// a chain of ~30 dependent L2 round trips: 4.7 + 7.1 us per pair in the step's launch list, 5.5 + 20 us with cold
+// caches (profiles/launches_r02_step.md, ncu_r02_cl_site.md), 212 launches per step; an 8-lane version of that pair
+// measured 4.4 + 9.3 us cold.  The running-statistic EMA follows
+// the aliasing class found on the host: all domains on ONE buffer pair (the shipped models) -> one closed-form
+// read-modify-write r' = k^D r + m sum_d k^(D-1-d) s_d; all distinct -> every domain's warp updates its own buffers;
+// mixed -> the d == 0 warp applies the domains in order.  No atomics, fixed summation order.
+constexpr int kFinQ = 8;
 
 template <int NACC>
-__device__ __forceinline__ void split_sum(const float* __restrict__ base, int S, int lane8, float (&a)[NACC]) {
+__device__ __forceinline__ void column_row_sum(const float* __restrict__ col, int nrows, int W, float (&a)[NACC]) {
+  static_assert(NACC % 2 == 0, "accumulators are read as float2");
 #pragma unroll
-  for (int i = 0; i < NACC; ++i) a[i] = lane8 < S ? __ldcg(base + i) : 0.f;
+  for (int i = 0; i < NACC; ++i) a[i] = 0.f;
+#pragma unroll 4
+  for (int r = threadIdx.x; r < nrows; r += 32) {
+    const float2* p = reinterpret_cast<const float2*>(col + (size_t)r * W);
 #pragma unroll
-  for (int o = 1; o < 8; o <<= 1)
+    for (int i = 0; i < NACC / 2; ++i) {
+      const float2 v = __ldcg(p + i);
+      a[2 * i] += v.x; a[2 * i + 1] += v.y;
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
 #pragma unroll
     for (int i = 0; i < NACC; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
 }
 
 template <int GS>
-__global__ void __launch_bounds__(8 * kFinG * DWT_MAX_DOMAINS) cl_fwd_finalize_kernel(const float* __restrict__ red, int S, const float* __restrict__ shift,
-                                                                                     const Geom gm, const FwdFin fin) {
+__global__ void __launch_bounds__(32 * kFinQ * DWT_MAX_DOMAINS) cl_fwd_finalize_kernel(const float* __restrict__ partial, int nrows, const float* __restrict__ shift,
+                                                                                      const Geom gm, const FwdFin fin) {
   using SH = ClShape<GS>;
   constexpr int NST = GS + GS * GS;
-  __shared__ float sStat[DWT_MAX_DOMAINS][kFinG][NST + 1];
-  __shared__ unsigned char sBad[DWT_MAX_DOMAINS][kFinG];
-  const int k8 = threadIdx.x & 7, gl = threadIdx.x >> 3, d = threadIdx.y, g = blockIdx.x * kFinG + gl;
+  __shared__ float sStat[DWT_MAX_DOMAINS][kFinQ][SH::NSUB][NST + 1];
+  __shared__ unsigned char sBad[DWT_MAX_DOMAINS][kFinQ][SH::NSUB];
+  const int ql = threadIdx.y, d = threadIdx.z, q = blockIdx.x * blockDim.y + ql;
   const int W = (gm.C >> 2) * SH::FWD;
   const float invM = 1.f / gm.M;
-  const bool own = g < gm.G;
-  float a[SH::FWD1];
-  split_sum<SH::FWD1>(red + ((size_t)d * S + (k8 < S ? k8 : 0)) * W + acc_index<GS, SH::FWD1>(own ? g : 0, 0), S, k8, a);
-  float mean[GS], cov[GS][GS];
-  bool bad = false;
-  if (own && k8 == 0) {
+  float a[SH::FWD];
+  column_row_sum<SH::FWD>(partial + (size_t)d * nrows * W + (size_t)q * SH::FWD, nrows, W, a);
+  const bool lead = threadIdx.x == 0;
+  const bool direct = gm.D == 1 || fin.aliased == 0;       // this domain owns its buffers
+  if (lead) {
 #pragma unroll
-    for (int i = 0; i < GS; ++i) mean[i] = shift[(size_t)d * gm.C + g * GS + i] + a[i] * invM;
+    for (int s = 0; s < SH::NSUB; ++s) {
+      const int g = q * SH::NSUB + s;
+      float mean[GS], cov[GS][GS];
 #pragma unroll
-    for (int i = 0; i < GS; ++i)
-#pragma unroll
-      for (int j = 0; j <= i; ++j) {
-        const float c = a[GS + i * (i + 1) / 2 + j] * invM - (a[i] * invM) * (a[j] * invM);
-        cov[i][j] = c; cov[j][i] = c;
-      }
-    bad = factor_thread<GS>(gm, fin, d, g, mean, cov, false);
-  }
-  if (!fin.update_running) return;
-  if (gm.D == 1 || fin.aliased == 0) {            // this domain owns its buffers
-    if (own && k8 == 0 && !bad) {
-      float cf[GS * GS];
+      for (int i = 0; i < GS; ++i) mean[i] = shift[(size_t)d * gm.C + g * GS + i] + a[s * SH::FWD1 + i] * invM;
 #pragma unroll
       for (int i = 0; i < GS; ++i)
 #pragma unroll
-        for (int j = 0; j < GS; ++j) cf[i * GS + j] = cov[i][j];
-      ema_direct<GS>(gm, fin, d, g, mean, cf);
-    }
-    return;
-  }
-  if (own && k8 == 0) {
-    sBad[d][gl] = bad ? 1 : 0;
+        for (int j = 0; j <= i; ++j) {
+          const float c = a[s * SH::FWD1 + GS + i * (i + 1) / 2 + j] * invM - (a[s * SH::FWD1 + i] * invM) * (a[s * SH::FWD1 + j] * invM);
+          cov[i][j] = c; cov[j][i] = c;
+        }
+      const bool bad = factor_thread<GS>(gm, fin, d, g, mean, cov, false);
+      if (fin.update_running) {
+        if (direct) {
+          if (!bad) {
+            float cf[GS * GS];
 #pragma unroll
-    for (int i = 0; i < GS; ++i) {
-      sStat[d][gl][i] = mean[i];
+            for (int i = 0; i < GS; ++i)
 #pragma unroll
-      for (int j = 0; j < GS; ++j) sStat[d][gl][GS + i * GS + j] = cov[i][j];
+              for (int j = 0; j < GS; ++j) cf[i * GS + j] = cov[i][j];
+            ema_direct<GS>(gm, fin, d, g, mean, cf);
+          }
+        } else {
+          sBad[d][ql][s] = bad ? 1 : 0;
+#pragma unroll
+          for (int i = 0; i < GS; ++i) {
+            sStat[d][ql][s][i] = mean[i];
+#pragma unroll
+            for (int j = 0; j < GS; ++j) sStat[d][ql][s][GS + i * GS + j] = cov[i][j];
+          }
+        }
+      }
     }
   }
+  if (!fin.update_running || direct) return;
   __syncthreads();
-  if (!(own && k8 == 0 && d == 0)) return;
-  if (fin.aliased == 1) {
-    // one shared buffer pair: D sequential updates collapse to r' = k^n r + m sum_d k^(later good domains) s_d
-    const float m = fin.momentum, kk = 1.f - fin.momentum;
-    float* rc = fin.rcov[0] + (size_t)g * GS * GS;
-    float* rm = fin.rmean[0] + g * GS;
-    float c[GS * GS], u[GS];
+  if (!(lead && d == 0)) return;
 #pragma unroll
-    for (int e = 0; e < GS * GS; ++e) c[e] = rc[e];
+  for (int s = 0; s < SH::NSUB; ++s) {
+    const int g = q * SH::NSUB + s;
+    if (fin.aliased == 1) {
+      // one shared buffer pair: the D sequential updates collapse to one read-modify-write
+      const float m = fin.momentum, kk = 1.f - fin.momentum;
+      float* rc = fin.rcov[0] + (size_t)g * GS * GS;
+      float* rm = fin.rmean[0] + g * GS;
+      float c[GS * GS], u[GS];
 #pragma unroll
-    for (int e = 0; e < GS; ++e) u[e] = rm[e];
-    for (int dd = 0; dd < gm.D; ++dd) {
-      if (sBad[dd][gl]) continue;
+      for (int e = 0; e < GS * GS; ++e) c[e] = rc[e];
 #pragma unroll
-      for (int e = 0; e < GS * GS; ++e) c[e] = m * (sStat[dd][gl][GS + e] * fin.unbias) + kk * c[e];
+      for (int e = 0; e < GS; ++e) u[e] = rm[e];
+      for (int dd = 0; dd < gm.D; ++dd) {
+        if (sBad[dd][ql][s]) continue;
 #pragma unroll
-      for (int e = 0; e < GS; ++e) u[e] = m * sStat[dd][gl][e] + kk * u[e];
+        for (int e = 0; e < GS * GS; ++e) c[e] = m * (sStat[dd][ql][s][GS + e] * fin.unbias) + kk * c[e];
+#pragma unroll
+        for (int e = 0; e < GS; ++e) u[e] = m * sStat[dd][ql][s][e] + kk * u[e];
+      }
+#pragma unroll
+      for (int e = 0; e < GS * GS; ++e) rc[e] = c[e];
+#pragma unroll
+      for (int e = 0; e < GS; ++e) rm[e] = u[e];
+    } else {
+      for (int dd = 0; dd < gm.D; ++dd)               // mixed aliasing: plain ordered read-modify-write
+        if (!sBad[dd][ql][s]) ema_direct<GS>(gm, fin, dd, g, &sStat[dd][ql][s][0], &sStat[dd][ql][s][GS]);
     }
-#pragma unroll
-    for (int e = 0; e < GS * GS; ++e) rc[e] = c[e];
-#pragma unroll
-    for (int e = 0; e < GS; ++e) rm[e] = u[e];
-    return;
   }
-  for (int dd = 0; dd < gm.D; ++dd)                 // mixed aliasing: plain ordered read-modify-write
-    if (!sBad[dd][gl]) ema_direct<GS>(gm, fin, dd, g, &sStat[dd][gl][0], &sStat[dd][gl][GS]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -436,41 +432,39 @@ __global__ void __launch_bounds__(kT, 2) cl_bwd_reduce_kernel(const float* __res
   }
 }
 
-// Same thread arrangement as the forward finalize (8 lanes add the split rows of one (group, domain), lane 0 does the
-// algebra); dgamma / dbeta are summed over the domains by the d == 0 lane after the barrier.
+// Same arrangement as the forward finalize (one warp per (float4 column, domain)); dgamma / dbeta are summed over the
+// domains by the d == 0 warp after the barrier.
 template <int GS>
-__global__ void __launch_bounds__(8 * kFinG * DWT_MAX_DOMAINS) cl_bwd_finalize_kernel(const float* __restrict__ red, int S, const Geom gm, const BwdFin fin) {
+__global__ void __launch_bounds__(32 * kFinQ * DWT_MAX_DOMAINS) cl_bwd_finalize_kernel(const float* __restrict__ partial, int nrows, const Geom gm, const BwdFin fin) {
   using SH = ClShape<GS>;
-  const int k8 = threadIdx.x & 7, gl = threadIdx.x >> 3, d = threadIdx.y, g = blockIdx.x * kFinG + gl;
+  const int d = threadIdx.z, q = blockIdx.x * blockDim.y + threadIdx.y;
   const int W = (gm.C >> 2) * SH::BWD;
-  const bool own = g < gm.G;
-  float a[SH::BWD1];
-  if (red != nullptr) {
-    split_sum<SH::BWD1>(red + ((size_t)d * S + (k8 < S ? k8 : 0)) * W + acc_index<GS, SH::BWD1>(own ? g : 0, 0), S, k8, a);
-  } else {
+  float a[SH::BWD];
+  column_row_sum<SH::BWD>(partial + (size_t)d * nrows * W + (size_t)q * SH::BWD, nrows, W, a);
+  const bool lead = threadIdx.x == 0;
+  if (lead) {
 #pragma unroll
-    for (int i = 0; i < SH::BWD1; ++i) a[i] = 0.f;
-  }
-  if (own && k8 == 0) {
-    float R[GS][GS], sdz[GS];
+    for (int s = 0; s < SH::NSUB; ++s) {
+      float R[GS][GS], sdz[GS];
 #pragma unroll
-    for (int i = 0; i < SH::BWD1; ++i) {
-      if (i < GS * GS) R[i / GS][i % GS] = a[i]; else sdz[i - GS * GS] = a[i];
+      for (int i = 0; i < SH::BWD1; ++i) {
+        if (i < GS * GS) R[i / GS][i % GS] = a[s * SH::BWD1 + i]; else sdz[i - GS * GS] = a[s * SH::BWD1 + i];
+      }
+      bwd_finalize_thread<GS>(gm, fin, d, q * SH::NSUB + s, R, sdz, false);
     }
-    bwd_finalize_thread<GS>(gm, fin, d, g, R, sdz, false);
   }
   if (!((fin.epi & DWT_EPI_AFFINE) && fin.dgamma != nullptr)) return;
   __syncthreads();                                  // the block's dgb_part writes (global) are visible block-wide
-  if (own && k8 == 0 && d == 0) {
+  if (lead && d == 0) {
 #pragma unroll
-    for (int i = 0; i < GS; ++i) {
+    for (int i = 0; i < 4; ++i) {                   // the column's 4 channels = NSUB groups x GS
       float sg = 0.f, sb = 0.f;
       for (int dd = 0; dd < gm.D; ++dd) {
-        sg += fin.dgb_part[((size_t)dd * 2 + 0) * gm.C + g * GS + i];
-        sb += fin.dgb_part[((size_t)dd * 2 + 1) * gm.C + g * GS + i];
+        sg += fin.dgb_part[((size_t)dd * 2 + 0) * gm.C + 4 * q + i];
+        sb += fin.dgb_part[((size_t)dd * 2 + 1) * gm.C + 4 * q + i];
       }
-      fin.dgamma[g * GS + i] = sg;
-      fin.dbeta[g * GS + i] = sb;
+      fin.dgamma[4 * q + i] = sg;
+      fin.dbeta[4 * q + i] = sb;
     }
   }
 }
@@ -605,11 +599,10 @@ int cl_bwd_width(int C, int GS) { return (C / 4) * (4 / GS) * (GS * GS + GS); }
 void cl_stats(const float* x, const Geom& gm, int nctas, int gz, float* partial, float* shift, cudaStream_t st) {
   CL_GS(gm.GS, (cl_stats_kernel<kGS><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, gm, partial, shift)));
 }
-void cl_vec_reduce(const float* partial, int nrows, int W, int D, int S, float* out, cudaStream_t st) {
-  vec_reduce_kernel<<<dim3((W + 63) / 64, D, S), 256, 0, st>>>(partial, nrows, W, out);
-}
-void cl_fwd_finalize(const float* red, int S, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st) {
-  CL_GS(gm.GS, (cl_fwd_finalize_kernel<kGS><<<(gm.G + kFinG - 1) / kFinG, dim3(8 * kFinG, gm.D), 0, st>>>(red, S, shift, gm, fin)));
+inline dim3 fin_block(const Geom& gm) { const int c4 = gm.C / 4; return dim3(32, c4 < kFinQ ? c4 : kFinQ, gm.D); }
+void cl_fwd_finalize(const float* partial, int nrows, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st) {
+  const dim3 b = fin_block(gm);
+  CL_GS(gm.GS, (cl_fwd_finalize_kernel<kGS><<<(gm.C / 4) / b.y, b, 0, st>>>(partial, nrows, shift, gm, fin)));
 }
 void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
               const float* gamma, const float* beta, const float* residual, uint8_t* mask, cudaStream_t st) {
@@ -623,8 +616,9 @@ void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas,
                    const float* gamma, const float* beta, const uint8_t* mask, float* partial, cudaStream_t st) {
   CL_GS(gm.GS, CL_EPI_BWD(epi, (cl_bwd_reduce_kernel<kGS, kEPI><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, dout, gm, mean, w, gamma, beta, mask, partial))));
 }
-void cl_bwd_finalize(const float* red, int S, const Geom& gm, const BwdFin& fin, cudaStream_t st) {
-  CL_GS(gm.GS, (cl_bwd_finalize_kernel<kGS><<<(gm.G + kFinG - 1) / kFinG, dim3(8 * kFinG, gm.D), 0, st>>>(red, S, gm, fin)));
+void cl_bwd_finalize(const float* partial, int nrows, const Geom& gm, const BwdFin& fin, cudaStream_t st) {
+  const dim3 b = fin_block(gm);
+  CL_GS(gm.GS, (cl_bwd_finalize_kernel<kGS><<<(gm.C / 4) / b.y, b, 0, st>>>(partial, nrows, gm, fin)));
 }
 void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, int gz, int epi, const float* coef,
                   const float* mean, const float* w, const float* gamma, const float* beta, const uint8_t* mask, float* dres,

@@ -90,51 +90,49 @@ __device__ __forceinline__ void store_block(float* M, const Blk& t, const float 
     for (int s = 0; s < 4; ++s) M[(4 * t.bi + r) * LDS + 4 * t.bj + s] = c[r][s];
 }
 
-// In-register right-looking Cholesky of the SPD matrix held as 4x4 blocks (a); on exit the lower
-// triangle of a holds L.  sCol[2][64] / sPiv[2] are the broadcast buffers.  False on a bad pivot.
-__device__ __forceinline__ bool cholesky_blocked(float (&a)[4][4], int GS, const Blk& t, float (*sCol)[kSB],
-                                                 float* sPiv) {
+// In-register right-looking Cholesky of the SPD matrix held as 4x4 blocks.  The blocks are held TRANSPOSED:
+// a[r][s] is element (i = 4*bj + s, j = 4*bi + r) -- for the symmetric input the same numbers as the (bi, bj) block, so
+// the caller fills `a` as if it were untransposed -- which puts the 16 owners of a COLUMN block (fixed bi) into one
+// half-warp: the pivot travels by shuffle and a step needs ONE block barrier (publish the scaled column, then every
+// thread applies the rank-1 update from the double-buffered sCol), not two (round 1: pivot through shared memory,
+// 128 barriers for a 64 x 64 group; profiles/ncu_r01i_tc_final.txt put 42 % of the kernel there).
+// On exit the entries with i >= j hold L[i][j].  False on a non-positive pivot.
+__device__ __forceinline__ bool cholesky_blocked(float (&a)[4][4], int GS, const Blk& t, float (*sCol)[kSB]) {
   bool ok = true;
-  if (threadIdx.x == 0) sPiv[0] = a[0][0];
-  __syncthreads();
+  const unsigned hmask = (threadIdx.x & 16) ? 0xFFFF0000u : 0x0000FFFFu;
   for (int k = 0; k < GS; ++k) {
     const int kb = k >> 2, kk = k & 3, buf = k & 1;
-    if (t.act && t.bj == kb) {                      // owners of column k: scale it, publish it
-      const float piv = sPiv[buf];
-      ok = ok && (piv > 0.f);
-      const float d = sqrtf(piv), inv = 1.f / d;
+    if (t.bi == kb) {                               // the half-warp that owns column k (j == k  <=>  r == kk)
+      float pv = 0.f;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int i = 4 * t.bi + r;
+      for (int q = 0; q < 4; ++q)
+        if (q == kk) pv = a[q][q];                  // meaningful in the diagonal thread bj == kb
+      pv = __shfl_sync(hmask, pv, kb, 16);
+      ok = ok && (pv > 0.f);
+      const float d = sqrtf(pv), inv = 1.f / d;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c == kk) {
-            float v = a[r][c];
+      for (int s = 0; s < 4; ++s) {
+        const int i = 4 * t.bj + s;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (r == kk) {
+            float v = a[r][s];
             v = (i > k) ? v * inv : ((i == k) ? d : v);
-            a[r][c] = v;
+            a[r][s] = v;
             sCol[buf][i] = (i > k) ? v : 0.f;
           }
       }
     }
     __syncthreads();
-    if (t.act) {                                    // rank-1 update of the trailing matrix
+    if (t.act) {                                    // rank-1 update of the trailing matrix (sCol is 0 for rows <= k)
       float ci[4], cj[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) { ci[r] = sCol[buf][4 * t.bi + r]; cj[r] = sCol[buf][4 * t.bj + r]; }
+      for (int q = 0; q < 4; ++q) { ci[q] = sCol[buf][4 * t.bj + q]; cj[q] = sCol[buf][4 * t.bi + q]; }
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int s = 0; s < 4; ++s) a[r][s] = fmaf(-ci[r], cj[s], a[r][s]);     // sCol is 0 for rows <= k
-      if (k + 1 < GS && t.bi == ((k + 1) >> 2) && t.bj == t.bi) {
-        const int q = (k + 1) & 3;
-        float pv = 0.f;
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-          if (r == q) pv = a[r][r];
-        sPiv[buf ^ 1] = pv;
-      }
+        for (int s = 0; s < 4; ++s) a[r][s] = fmaf(-cj[r], ci[s], a[r][s]);
     }
-    __syncthreads();
   }
   return ok;
 }
@@ -200,7 +198,7 @@ __global__ void __launch_bounds__(256) fwd_factor_kernel(const float* __restrict
   float* sW = sL + kMat;           // its inverse
   float* sT = sW + kMat;           // scratch of the inverse
   float* sC = sT + kMat;           // un-shrunk covariance (for the EMA)
-  __shared__ float sCol[2][kSB], sPiv[2], sMean[kSB];
+  __shared__ float sCol[2][kSB], sMean[kSB];
   __shared__ int sBad, sBadDom;
   const int g = blockIdx.x, GS = gm.GS, nb = kSB / GS, sb = g / nb, o = (g % nb) * GS;
   const Blk t(GS);
@@ -235,29 +233,40 @@ __global__ void __launch_bounds__(256) fwd_factor_kernel(const float* __restrict
         }
         a[r][s] = v;
       }
+    // the running buffers of this domain are fetched NOW (their latency hides behind the factorisation); the previous
+    // domain's stores precede this point by a block barrier, so aliased buffers still see the ordered sequence
+    constexpr int kEmaPer = kSB * kSB / 256;
+    float rc_old[kEmaPer], rm_old = 0.f;
+    const bool ema = G != nullptr && f.update_running;
+    if (ema) {
+#pragma unroll
+      for (int n = 0; n < kEmaPer; ++n) {
+        const int e = threadIdx.x + 256 * n;
+        rc_old[n] = e < GS * GS ? f.rcov[d][(size_t)g * GS * GS + e] : 0.f;
+      }
+      if ((int)threadIdx.x < GS) rm_old = f.rmean[d][g * GS + threadIdx.x];
+    }
     if (threadIdx.x == 0) sBadDom = 0;
     __syncthreads();
-    if (!cholesky_blocked(a, GS, t, sCol, sPiv)) { sBad = 1; sBadDom = 1; }
-    if (t.act) {
+    if (!cholesky_blocked(a, GS, t, sCol)) { sBad = 1; sBadDom = 1; }
+    if (t.act) {                                    // a[r][s] = element (i = 4bj+s, j = 4bi+r): keep the lower triangle
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int s = 0; s < 4; ++s)
-          sL[(4 * t.bi + r) * LDS + 4 * t.bj + s] = (4 * t.bj + s <= 4 * t.bi + r) ? a[r][s] : 0.f;
+          sL[(4 * t.bj + s) * LDS + 4 * t.bi + r] = (4 * t.bi + r <= 4 * t.bj + s) ? a[r][s] : 0.f;
     }
     __syncthreads();
     tri_inverse(sL, sW, sT, GS);
     for (int e = threadIdx.x; e < GS * GS; e += blockDim.x) f.save_w[gbase + e] = sW[(e / GS) * LDS + e % GS];
-    if (G && f.update_running && !sBadDom) {       // a non-PD batch covariance never reaches the running buffers
+    if (ema && !sBadDom) {                         // a non-PD batch covariance never reaches the running buffers
       const float m = f.momentum, k = 1.f - f.momentum;
-      for (int e = threadIdx.x; e < GS * GS; e += blockDim.x) {
-        float* p = f.rcov[d] + (size_t)g * GS * GS + e;
-        *p = m * (sC[(e / GS) * LDS + e % GS] * f.unbias) + k * (*p);
+#pragma unroll
+      for (int n = 0; n < kEmaPer; ++n) {
+        const int e = threadIdx.x + 256 * n;
+        if (e < GS * GS) f.rcov[d][(size_t)g * GS * GS + e] = m * (sC[(e / GS) * LDS + e % GS] * f.unbias) + k * rc_old[n];
       }
-      for (int i = threadIdx.x; i < GS; i += blockDim.x) {
-        float* p = f.rmean[d] + g * GS + i;
-        *p = m * sMean[i] + k * (*p);
-      }
+      if ((int)threadIdx.x < GS) f.rmean[d][g * GS + threadIdx.x] = m * sMean[threadIdx.x] + k * rm_old;
     }
     __syncthreads();      // also orders this domain's buffer writes before the next domain's reads (aliasing)
   }

@@ -207,14 +207,16 @@ def test_resnet_224_vs_reference_golden(fmt, site_mode, dev):
     with torch.no_grad():
         e["logits_eval"] = both(n(model(x)), z["logits_eval"])
     print(fmt, site_mode, {k: ("%.2e" % v[0], "%.2e" % v[1]) for k, v in e.items()})
-    assert e["logits"][0] < max(1e-3, 2 * e["yard_logits"][0]) and e["logits"][1] < max(5e-3, 2 * e["yard_logits"][1])
+    # measured on B200: 2e-5 norm-wise / 3e-5 max-elementwise in all three builds (the ATen restatement: the same)
+    assert e["logits"][0] < 2e-4 and e["logits"][1] < 5e-4, e["logits"]
     assert abs(cls.item() - float(z["cls_loss"])) < 2e-3 and abs(mec.item() - float(z["mec_loss"])) < 2e-3
     for k in [k for k in e if k.startswith("grad/")]:
         yard = e["yard/" + k[5:]][0]
-        assert e[k][0] < max(1e-2, 2 * yard), (k, e[k], yard)
+        assert e[k][0] < max(1e-2, 1.5 * yard), (k, e[k], yard)       # measured: 2e-2 for both (cuDNN vs MKLDNN golden)
     for k in [k for k in e if k.startswith("buf/")]:
         assert e[k][0] < 1e-3, (k, e[k])
-    assert e["logits_eval"][0] < 2e-3
+    assert e["logits_eval"][0] < 5e-4, e["logits_eval"]
+    assert e["gradnorms"][0] < 5e-3, e["gradnorms"]                           # measured 5e-4 .. 7e-4
 
 
 # --------------------------------------------------------------------------- residual tail: byte map vs out > 0

@@ -1,7 +1,7 @@
 #!/bin/bash
-# round-2 GPU call G (1 GPU): reworked max-pool kernels, step time, launch list of the current build
+# round-2 GPU call G (1 GPU): row-CTA max-pool kernels + warp-per-column finalize (vec_reduce merged): parity, step time, launch list
 mkdir -p gpurun_out/g
-timeout 300 python -m pytest tests/test_gpu_parity_r2.py -m gpu -q -p no:cacheprovider -k "maxpool or resnet_224" > gpurun_out/g/pytest_pool.log 2>&1; echo "pytest pool rc=$?"; tail -2 gpurun_out/g/pytest_pool.log
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/g/pytest_all.log 2>&1; echo "pytest all rc=$?"; tail -4 gpurun_out/g/pytest_all.log
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras --sites-out gpurun_out/g/sites.json > gpurun_out/g/bench_1gpu.json 2> gpurun_out/g/bench_1gpu.err; echo "1gpu rc=$?"
 python - <<'PY'
 import json
@@ -14,3 +14,4 @@ for n in ("bench_1gpu",):
         print(n, "failed", e)
 PY
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/g/launches_ours.csv python tools/one_step.py > gpurun_out/g/ncu_ours.log 2>&1; echo "ncu ours rc=$?"
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/g/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/g/smoke.log
