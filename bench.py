@@ -217,6 +217,13 @@ class FlatGradAllReduce:
     def reduce(self):
         if self.world <= 1:
             return
+        if len(self.ranges) == 1:                    # one collective after backward (round-1 behaviour)
+            if self.flat.is_cuda:
+                self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.AVG)
+            else:
+                self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM)
+                self.flat.div_(self.world)
+            return
         for k in range(len(self.ranges) - 1, -1, -1):   # whatever backward did not complete (unused parameters), in a
             if not self.launched[k]:                     # fixed order on every rank
                 self._launch(k)
@@ -278,7 +285,10 @@ def run_reference(args):
         "impl": "reference", "metric": "ResNet-50-DWT images/sec fwd+bwd", "value": val, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, per_domain=per_domain, site_mode="modules"),
+        "config": workload_config(args, per_domain=args.per_domain),
+        "implementation": {"site_mode": "modules (the reference's split -> 3 modules -> cat -> affine -> relu composition)",
+                           "memory_format": "nchw", "launch": "eager, CPU",
+                           "sample": f"each step is 3x{per_domain} images of the 3x{args.per_domain}-image workload step"},
         "whole_job": "one host: rank 0 alone runs; images/s of this host, independent of --gpus",
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
@@ -320,15 +330,23 @@ def run_reference_micro(args, port, cores):
     }))
 
 
-def workload_config(args, per_domain, site_mode):
+def workload_config(args, per_domain):
+    """The WORKLOAD both arms are quoted on (BASELINE.json configs[2] / [3] at --gpus N): identical in the GPU arm's line
+    and in the reference arm's line.  How each arm runs it (layout, fused sites, CUDA graph, collective; the CPU arm's
+    bounded sample) is in the line's `implementation` / `cpu_baseline.sample`, not here."""
     return {"workload": "ResNet-50-DWT synthetic Office-Home 224x224, train step = fwd + NLL + 0.1*MEC + bwd + SGD",
             "per_domain_batch": per_domain, "images_per_gpu": 3 * per_domain, "global_images": 3 * per_domain * args.gpus,
-            "group_size": 4, "site_mode": site_mode, "memory_format": getattr(args, "memory_format", "nchw"),
-            "parallelism": f"dp{args.gpus}",
-            "grad_sync": (f"flat fp32 gradient buffer, NCCL all-reduce (AVG) in {getattr(args, 'grad_segments', 1)} segment(s) "
-                          "issued as backward completes them (layer4+fc, layer3, rest), overlapped with the remaining backward"),
-            "l2": "no explicit flush: per-step working set (activations) is tens of GB >> 126 MB L2",
-            "launch": "CUDA-graph replay of the whole step" if getattr(args, "cuda_graph", False) and getattr(args, "impl", "ours") == "ours" else "eager"}
+            "group_size": 4, "parallelism": f"dp{args.gpus}",
+            "l2": "no explicit flush: per-step working set (activations) is tens of GB >> 126 MB L2"}
+
+
+def implementation_note(args):
+    seg = getattr(args, "grad_segments", 1)
+    return {"site_mode": args.site_mode, "memory_format": args.memory_format,
+            "launch": "CUDA-graph replay of the whole step" if args.cuda_graph else "eager",
+            "grad_sync": ("flat fp32 gradient buffer, one NCCL all-reduce (AVG) per step after backward" if seg == 1 else
+                          f"flat fp32 gradient buffer, NCCL all-reduce (AVG) in {seg} segments issued as backward completes "
+                          "them (layer4+fc, layer3, rest), overlapped with the remaining backward")}
 
 
 def cpu_baseline(args, workload="resnet"):
@@ -660,7 +678,7 @@ def run_ours(args):
         "metric": "ResNet-50-DWT images/sec fwd+bwd", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, per_domain=B, site_mode=args.site_mode),
+        "config": workload_config(args, per_domain=B), "implementation": implementation_note(args),
         "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": host_images.numel() * 4 + host_labels.numel() * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "kernels": fams,
