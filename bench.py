@@ -150,26 +150,43 @@ class FlatGradAllReduce:
     (94.6 MB for ResNet-50-DWT), averaged over the ranks by NCCL over NVLink (gloo in the CPU test).  Whitening / BN
     statistics are never exchanged: every rank normalises its own minibatch.
 
+    gather="copy" (the default of bench.py, measured on 2 B200s: 31.48 vs 31.75 ms per step): autograd produces its own
+    gradient tensors, ONE multi-tensor copy moves them into the flat buffer after backward, ONE all-reduce averages it, and
+    .grad is re-pointed at the views for the optimizer -- instead of 161 small in-place accumulation kernels and a 94.6 MB
+    memset per step.  gather="accumulate": .grad are the views themselves; then the buffer can also be cut into
+    `segments` pieces that are all-reduced while backward is still running:
+
     The buffer is cut into `segments` contiguous pieces along the layer order and each piece is all-reduced as soon
     as backward has produced its last gradient (a post-accumulate hook per parameter counts them down): backward
     runs layer4 -> stem, so the big late-layer pieces (layer4 + fc = 60 MB, layer3 = 28 MB) travel while the earlier
     layers are still back-propagating and only the small stem / layer1 / layer2 piece (6 MB) is exposed at the end.
     The collectives are issued asynchronously on NCCL's own stream (async_op) and joined in reduce(); no Python runs
     at replay time -- the whole step, collectives and cross-stream edges included, is captured into the CUDA graph.
-    segments=1 is the round-1 behaviour: one all-reduce after backward."""
+    Measured on 2 B200s the overlap buys nothing there (32.79 ms with 3 segments vs 32.71 ms with one collective: a
+    60 MB all-reduce between two GPUs takes ~0.2 ms and its kernel competes with backward for SMs and HBM); it stays
+    available (--grad-gather accumulate --grad-segments 3) for larger rank counts."""
 
-    def __init__(self, model, world, segments=3):
+    def __init__(self, model, world, segments=3, gather="accumulate"):
         import torch.distributed as dist
-        self.world, self.dist = world, dist
+        self.world, self.dist, self.gather = world, dist, gather
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         params = [p for _, p in named]
+        self.params = params
         total = sum(p.numel() for p in params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
-        off, offsets = 0, []
+        off, offsets, self.views = 0, [], []
         for p in params:
-            p.grad = self.flat[off:off + p.numel()].as_strided(p.shape, p.stride())   # same memory format as p
+            self.views.append(self.flat[off:off + p.numel()].as_strided(p.shape, p.stride()))   # same memory format as p
             offsets.append(off)
             off += p.numel()
+        # gather = "accumulate": .grad IS the view, autograd adds into it (one small in-place add per parameter and a
+        # memset per step); "copy": autograd produces its own gradient tensors, ONE multi-tensor copy moves them into the
+        # flat buffer after backward and .grad is re-pointed at the views for the optimizer (needs segments == 1)
+        if gather == "copy":
+            segments = 1
+        else:
+            for p, v in zip(params, self.views):
+                p.grad = v
         # segment boundaries in layer order: [stem, layer1, layer2 | layer3 | layer4, fc_out] (fewer when asked)
         cuts = [0]
         if segments >= 3:
@@ -194,6 +211,10 @@ class FlatGradAllReduce:
                     p.register_post_accumulate_grad_hook(self._on_grad)
 
     def zero(self):
+        if self.gather == "copy":
+            for p in self.params:
+                p.grad = None
+            return
         self.flat.zero_()
         self.pending = [r[2] for r in self.ranges]
         self.launched = [False] * len(self.ranges)
@@ -215,6 +236,10 @@ class FlatGradAllReduce:
             self.works.append(self.dist.all_reduce(seg, op=self.dist.ReduceOp.SUM, async_op=True))
 
     def reduce(self):
+        if self.gather == "copy":
+            torch._foreach_copy_(self.views, [p.grad for p in self.params])
+            for p, v in zip(self.params, self.views):
+                p.grad = v
         if self.world <= 1:
             return
         if len(self.ranges) == 1:                    # one collective after backward (round-1 behaviour)
@@ -342,8 +367,11 @@ def workload_config(args, per_domain):
 
 def implementation_note(args):
     seg = getattr(args, "grad_segments", 1)
+    if getattr(args, "grad_gather", "accumulate") == "copy":
+        seg = 1
     return {"site_mode": args.site_mode, "memory_format": args.memory_format,
             "launch": "CUDA-graph replay of the whole step" if args.cuda_graph else "eager",
+            "grad_gather": getattr(args, "grad_gather", "accumulate"),
             "grad_sync": ("flat fp32 gradient buffer, one NCCL all-reduce (AVG) per step after backward" if seg == 1 else
                           f"flat fp32 gradient buffer, NCCL all-reduce (AVG) in {seg} segments issued as backward completes "
                           "them (layer4+fc, layer3, rest), overlapped with the remaining backward")}
@@ -488,7 +516,7 @@ def run_ours(args):
     nhwc = args.memory_format == "nhwc"
     model = build_model(dwt_b200, device, args.site_mode, channels_last=nhwc, stem_pad=args.stem_pad)
     net = model
-    sync = FlatGradAllReduce(model, world, segments=args.grad_segments) if distributed else None   # one GPU: plain .grad tensors
+    sync = FlatGradAllReduce(model, world, segments=args.grad_segments, gather=args.grad_gather) if distributed else None   # one GPU: plain .grad tensors
     opt = make_optimizer(model)
     mec = dwt_b200.MinEntropyConsensusLoss(NUM_CLASSES, device)
     head = dwt_b200.HeadLoss(NUM_CLASSES, LAMBDA_MEC)
@@ -811,6 +839,9 @@ def main():
     ap.add_argument("--sites-out", default="", help="write the per-site kernel table (JSON) here")
     ap.add_argument("--stem-pad", type=int, default=0, choices=[0, 4, 8],
                     help="zero-pad the 3-channel image (and the stem weight) to this many channels for cuDNN")
+    ap.add_argument("--grad-gather", choices=["accumulate", "copy"], default="copy",
+                    help="how gradients reach the flat all-reduce buffer: autograd accumulates into views of it, or one "
+                         "multi-tensor copy after backward")
     ap.add_argument("--grad-segments", type=int, default=1, choices=[1, 2, 3],
                     help="pieces the flat gradient buffer is all-reduced in (1 = one collective after backward)")
     ap.add_argument("--micro-n", type=int, default=256)

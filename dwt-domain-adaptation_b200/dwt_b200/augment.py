@@ -60,7 +60,7 @@ class PairedAugment:
 
         def dest(t):
             if t is None:
-                return torch.empty((b, 3, self.crop, self.crop), dtype=torch.float32, device=dev).contiguous(memory_format=fmt)
+                return torch.empty((b, 3, self.crop, self.crop), dtype=torch.float32, device=dev, memory_format=fmt)
             if t.shape != (b, 3, self.crop, self.crop) or t.dtype != torch.float32 or not t.is_contiguous(memory_format=fmt):
                 raise ValueError("output must be a float32 [B, 3, crop, crop] tensor dense in the requested memory format")
             nv.require_cuda(t)

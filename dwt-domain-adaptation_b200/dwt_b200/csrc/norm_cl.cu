@@ -195,6 +195,20 @@ __device__ __forceinline__ void column_row_sum(const float* __restrict__ col, in
     for (int i = 0; i < NACC; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
 }
 
+// After column_row_sum every lane holds the column's NSUB * PER totals; lane s < NSUB takes the PER values of group s
+// (selected with predicated moves: the NSUB groups of a column are then finalized by NSUB lanes in parallel, not one
+// after the other by lane 0 -- for batch norm, NSUB = 4, that was four dependent sqrt / divide / read-modify-write chains).
+template <int NSUB, int PER>
+__device__ __forceinline__ void take_group(const float (&a)[NSUB * PER], int s, float (&v)[PER]) {
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] = a[i];
+#pragma unroll
+    for (int k = 1; k < NSUB; ++k)
+      if (s == k) v[i] = a[k * PER + i];
+  }
+}
+
 template <int GS>
 __global__ void __launch_bounds__(32 * kFinQ * DWT_MAX_DOMAINS) cl_fwd_finalize_kernel(const float* __restrict__ partial, int nrows, const float* __restrict__ shift,
                                                                                       const Geom gm, const FwdFin fin) {
@@ -202,46 +216,57 @@ __global__ void __launch_bounds__(32 * kFinQ * DWT_MAX_DOMAINS) cl_fwd_finalize_
   constexpr int NST = GS + GS * GS;
   __shared__ float sStat[DWT_MAX_DOMAINS][kFinQ][SH::NSUB][NST + 1];
   __shared__ unsigned char sBad[DWT_MAX_DOMAINS][kFinQ][SH::NSUB];
-  const int ql = threadIdx.y, d = threadIdx.z, q = blockIdx.x * blockDim.y + ql;
+  const int s = threadIdx.x, ql = threadIdx.y, d = threadIdx.z, q = blockIdx.x * blockDim.y + ql;
   const int W = (gm.C >> 2) * SH::FWD;
   const float invM = 1.f / gm.M;
+  const bool lead = s < SH::NSUB;                          // lane s finalizes group q * NSUB + s
+  const int g = q * SH::NSUB + (lead ? s : 0);
+  const bool direct = gm.D == 1 || fin.aliased == 0;       // this domain owns its buffers
+  // the running buffers this lane will update are fetched first: their (DRAM) latency hides behind the row sums
+  const int dbuf = direct ? d : 0;
+  const bool upd = fin.update_running && lead && (direct || (fin.aliased == 1 && d == 0));
+  float rc_old[GS * GS], rm_old[GS];
+  if (upd) {
+#pragma unroll
+    for (int e = 0; e < GS * GS; ++e) rc_old[e] = fin.rcov[dbuf][(size_t)g * GS * GS + e];
+#pragma unroll
+    for (int e = 0; e < GS; ++e) rm_old[e] = fin.rmean[dbuf][g * GS + e];
+  }
   float a[SH::FWD];
   column_row_sum<SH::FWD>(partial + (size_t)d * nrows * W + (size_t)q * SH::FWD, nrows, W, a);
-  const bool lead = threadIdx.x == 0;
-  const bool direct = gm.D == 1 || fin.aliased == 0;       // this domain owns its buffers
   if (lead) {
+    float v[SH::FWD1];
+    take_group<SH::NSUB, SH::FWD1>(a, s, v);
+    float mean[GS], cov[GS][GS];
 #pragma unroll
-    for (int s = 0; s < SH::NSUB; ++s) {
-      const int g = q * SH::NSUB + s;
-      float mean[GS], cov[GS][GS];
+    for (int i = 0; i < GS; ++i) mean[i] = shift[(size_t)d * gm.C + g * GS + i] + v[i] * invM;
 #pragma unroll
-      for (int i = 0; i < GS; ++i) mean[i] = shift[(size_t)d * gm.C + g * GS + i] + a[s * SH::FWD1 + i] * invM;
+    for (int i = 0; i < GS; ++i)
 #pragma unroll
-      for (int i = 0; i < GS; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) {
-          const float c = a[s * SH::FWD1 + GS + i * (i + 1) / 2 + j] * invM - (a[s * SH::FWD1 + i] * invM) * (a[s * SH::FWD1 + j] * invM);
-          cov[i][j] = c; cov[j][i] = c;
-        }
-      const bool bad = factor_thread<GS>(gm, fin, d, g, mean, cov, false);
-      if (fin.update_running) {
-        if (direct) {
-          if (!bad) {
-            float cf[GS * GS];
-#pragma unroll
-            for (int i = 0; i < GS; ++i)
-#pragma unroll
-              for (int j = 0; j < GS; ++j) cf[i * GS + j] = cov[i][j];
-            ema_direct<GS>(gm, fin, d, g, mean, cf);
-          }
-        } else {
-          sBad[d][ql][s] = bad ? 1 : 0;
+      for (int j = 0; j <= i; ++j) {
+        const float c = v[GS + i * (i + 1) / 2 + j] * invM - (v[i] * invM) * (v[j] * invM);
+        cov[i][j] = c; cov[j][i] = c;
+      }
+    const bool bad = factor_thread<GS>(gm, fin, d, g, mean, cov, false);
+    if (fin.update_running) {
+      if (direct) {
+        if (!bad) {
+          const float m = fin.momentum, kk = 1.f - fin.momentum;
 #pragma unroll
           for (int i = 0; i < GS; ++i) {
-            sStat[d][ql][s][i] = mean[i];
+            fin.rmean[d][g * GS + i] = m * mean[i] + kk * rm_old[i];
 #pragma unroll
-            for (int j = 0; j < GS; ++j) sStat[d][ql][s][GS + i * GS + j] = cov[i][j];
+            for (int j = 0; j < GS; ++j)
+              fin.rcov[d][(size_t)g * GS * GS + i * GS + j] = m * (cov[i][j] * fin.unbias) + kk * rc_old[i * GS + j];
           }
+        }
+      } else {
+        sBad[d][ql][s] = bad ? 1 : 0;
+#pragma unroll
+        for (int i = 0; i < GS; ++i) {
+          sStat[d][ql][s][i] = mean[i];
+#pragma unroll
+          for (int j = 0; j < GS; ++j) sStat[d][ql][s][GS + i * GS + j] = cov[i][j];
         }
       }
     }
@@ -249,34 +274,25 @@ __global__ void __launch_bounds__(32 * kFinQ * DWT_MAX_DOMAINS) cl_fwd_finalize_
   if (!fin.update_running || direct) return;
   __syncthreads();
   if (!(lead && d == 0)) return;
+  if (fin.aliased == 1) {
+    // one shared buffer pair: the D sequential updates collapse to one read-modify-write
+    const float m = fin.momentum, kk = 1.f - fin.momentum;
+    float* rc = fin.rcov[0] + (size_t)g * GS * GS;
+    float* rm = fin.rmean[0] + g * GS;
+    for (int dd = 0; dd < gm.D; ++dd) {
+      if (sBad[dd][ql][s]) continue;
 #pragma unroll
-  for (int s = 0; s < SH::NSUB; ++s) {
-    const int g = q * SH::NSUB + s;
-    if (fin.aliased == 1) {
-      // one shared buffer pair: the D sequential updates collapse to one read-modify-write
-      const float m = fin.momentum, kk = 1.f - fin.momentum;
-      float* rc = fin.rcov[0] + (size_t)g * GS * GS;
-      float* rm = fin.rmean[0] + g * GS;
-      float c[GS * GS], u[GS];
+      for (int e = 0; e < GS * GS; ++e) rc_old[e] = m * (sStat[dd][ql][s][GS + e] * fin.unbias) + kk * rc_old[e];
 #pragma unroll
-      for (int e = 0; e < GS * GS; ++e) c[e] = rc[e];
-#pragma unroll
-      for (int e = 0; e < GS; ++e) u[e] = rm[e];
-      for (int dd = 0; dd < gm.D; ++dd) {
-        if (sBad[dd][ql][s]) continue;
-#pragma unroll
-        for (int e = 0; e < GS * GS; ++e) c[e] = m * (sStat[dd][ql][s][GS + e] * fin.unbias) + kk * c[e];
-#pragma unroll
-        for (int e = 0; e < GS; ++e) u[e] = m * sStat[dd][ql][s][e] + kk * u[e];
-      }
-#pragma unroll
-      for (int e = 0; e < GS * GS; ++e) rc[e] = c[e];
-#pragma unroll
-      for (int e = 0; e < GS; ++e) rm[e] = u[e];
-    } else {
-      for (int dd = 0; dd < gm.D; ++dd)               // mixed aliasing: plain ordered read-modify-write
-        if (!sBad[dd][ql][s]) ema_direct<GS>(gm, fin, dd, g, &sStat[dd][ql][s][0], &sStat[dd][ql][s][GS]);
+      for (int e = 0; e < GS; ++e) rm_old[e] = m * sStat[dd][ql][s][e] + kk * rm_old[e];
     }
+#pragma unroll
+    for (int e = 0; e < GS * GS; ++e) rc[e] = rc_old[e];
+#pragma unroll
+    for (int e = 0; e < GS; ++e) rm[e] = rm_old[e];
+  } else {
+    for (int dd = 0; dd < gm.D; ++dd)               // mixed aliasing: plain ordered read-modify-write
+      if (!sBad[dd][ql][s]) ema_direct<GS>(gm, fin, dd, g, &sStat[dd][ql][s][0], &sStat[dd][ql][s][GS]);
   }
 }
 
@@ -437,35 +453,30 @@ __global__ void __launch_bounds__(kT, 2) cl_bwd_reduce_kernel(const float* __res
 template <int GS>
 __global__ void __launch_bounds__(32 * kFinQ * DWT_MAX_DOMAINS) cl_bwd_finalize_kernel(const float* __restrict__ partial, int nrows, const Geom gm, const BwdFin fin) {
   using SH = ClShape<GS>;
-  const int d = threadIdx.z, q = blockIdx.x * blockDim.y + threadIdx.y;
+  const int s = threadIdx.x, d = threadIdx.z, q = blockIdx.x * blockDim.y + threadIdx.y;
   const int W = (gm.C >> 2) * SH::BWD;
   float a[SH::BWD];
   column_row_sum<SH::BWD>(partial + (size_t)d * nrows * W + (size_t)q * SH::BWD, nrows, W, a);
-  const bool lead = threadIdx.x == 0;
-  if (lead) {
+  if (s < SH::NSUB) {                               // lane s finalizes group q * NSUB + s
+    float v[SH::BWD1], R[GS][GS], sdz[GS];
+    take_group<SH::NSUB, SH::BWD1>(a, s, v);
 #pragma unroll
-    for (int s = 0; s < SH::NSUB; ++s) {
-      float R[GS][GS], sdz[GS];
-#pragma unroll
-      for (int i = 0; i < SH::BWD1; ++i) {
-        if (i < GS * GS) R[i / GS][i % GS] = a[s * SH::BWD1 + i]; else sdz[i - GS * GS] = a[s * SH::BWD1 + i];
-      }
-      bwd_finalize_thread<GS>(gm, fin, d, q * SH::NSUB + s, R, sdz, false);
+    for (int i = 0; i < SH::BWD1; ++i) {
+      if (i < GS * GS) R[i / GS][i % GS] = v[i]; else sdz[i - GS * GS] = v[i];
     }
+    bwd_finalize_thread<GS>(gm, fin, d, q * SH::NSUB + s, R, sdz, false);
   }
   if (!((fin.epi & DWT_EPI_AFFINE) && fin.dgamma != nullptr)) return;
   __syncthreads();                                  // the block's dgb_part writes (global) are visible block-wide
-  if (lead && d == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {                   // the column's 4 channels = NSUB groups x GS
-      float sg = 0.f, sb = 0.f;
-      for (int dd = 0; dd < gm.D; ++dd) {
-        sg += fin.dgb_part[((size_t)dd * 2 + 0) * gm.C + 4 * q + i];
-        sb += fin.dgb_part[((size_t)dd * 2 + 1) * gm.C + 4 * q + i];
-      }
-      fin.dgamma[4 * q + i] = sg;
-      fin.dbeta[4 * q + i] = sb;
+  if (d == 0 && s < 4) {                            // lane i sums channel 4q + i over the domains
+    const int ch = 4 * q + s;
+    float sg = 0.f, sb = 0.f;
+    for (int dd = 0; dd < gm.D; ++dd) {
+      sg += fin.dgb_part[((size_t)dd * 2 + 0) * gm.C + ch];
+      sb += fin.dgb_part[((size_t)dd * 2 + 1) * gm.C + ch];
     }
+    fin.dgamma[ch] = sg;
+    fin.dbeta[ch] = sb;
   }
 }
 

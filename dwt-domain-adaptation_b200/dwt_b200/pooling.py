@@ -24,7 +24,7 @@ class _MaxPoolFunction(torch.autograd.Function):
                                  f"got shape {tuple(x.shape)}, strides {tuple(x.stride())}")
         n, c, h, w = x.shape
         oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
-        y = torch.empty((n, c, oh, ow), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
+        y = torch.empty((n, c, oh, ow), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
         idx = torch.empty(n * oh * ow * c, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             nv.check(lib.dwt_maxpool_fwd(nv.ptr(x), nv.ptr(y), nv.ptr(idx), n, h, w, c, k, s, p, nv.stream_ptr(dev)))
@@ -39,7 +39,7 @@ class _MaxPoolFunction(torch.autograd.Function):
         n, c, h, w, k, s, p = ctx.cfg
         dy = dy.contiguous(memory_format=torch.channels_last)
         dev = nv.require_cuda(dy)
-        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
         with torch.cuda.device(dev):
             nv.check(lib.dwt_maxpool_bwd(nv.ptr(dy), nv.ptr(idx), nv.ptr(dx), n, h, w, c, k, s, p, nv.stream_ptr(dev)))
         return dx, None, None, None
