@@ -129,11 +129,12 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- model
-def build_model(layers, device, site_mode, seed=1, channels_last=False, stem_pad=0):
+def build_model(layers, device, site_mode, seed=1, channels_last=False, stem_pad=0, stem_nchw=False):
     from harness.resnet50_dwt import build_resnet50_dwt
     from harness.synth import synth_state_dict
     sd = {k: v.to(device) for k, v in synth_state_dict(seed=seed).items()}
-    model = build_resnet50_dwt(sd, layers, site_mode=site_mode, channels_last=channels_last, stem_pad=stem_pad).to(device)
+    model = build_resnet50_dwt(sd, layers, site_mode=site_mode, channels_last=channels_last, stem_pad=stem_pad,
+                               stem_nchw=stem_nchw).to(device)
     return model.train()
 
 
@@ -514,7 +515,7 @@ def run_ours(args):
         return
 
     nhwc = args.memory_format == "nhwc"
-    model = build_model(dwt_b200, device, args.site_mode, channels_last=nhwc, stem_pad=args.stem_pad)
+    model = build_model(dwt_b200, device, args.site_mode, channels_last=nhwc, stem_pad=args.stem_pad, stem_nchw=args.stem_nchw)
     net = model
     sync = FlatGradAllReduce(model, world, segments=args.grad_segments, gather=args.grad_gather) if distributed else None   # one GPU: plain .grad tensors
     opt = make_optimizer(model)
@@ -839,6 +840,7 @@ def main():
     ap.add_argument("--sites-out", default="", help="write the per-site kernel table (JSON) here")
     ap.add_argument("--stem-pad", type=int, default=0, choices=[0, 4, 8],
                     help="zero-pad the 3-channel image (and the stem weight) to this many channels for cuDNN")
+    ap.add_argument("--stem-nchw", action="store_true", help="run only the 3-channel stem convolution in NCHW (experiment)")
     ap.add_argument("--grad-gather", choices=["accumulate", "copy"], default="copy",
                     help="how gradients reach the flat all-reduce buffer: autograd accumulates into views of it, or one "
                          "multi-tensor copy after backward")

@@ -173,7 +173,7 @@ __device__ __forceinline__ int acc_index(int g, int a) {
 // the aliasing class found on the host: all domains on ONE buffer pair (the shipped models) -> one closed-form
 // read-modify-write r' = k^D r + m sum_d k^(D-1-d) s_d; all distinct -> every domain's warp updates its own buffers;
 // mixed -> the d == 0 warp applies the domains in order.  No atomics, fixed summation order.
-constexpr int kFinQ = 8;
+constexpr int kFinQ = 2;   // few columns per block: many small blocks pull the partial rows from L2 in parallel
 
 template <int NACC>
 __device__ __forceinline__ void column_row_sum(const float* __restrict__ col, int nrows, int W, float (&a)[NACC]) {

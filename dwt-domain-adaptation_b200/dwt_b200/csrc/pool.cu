@@ -21,28 +21,40 @@ namespace dwt {
 namespace {
 
 struct PoolGeom {
-  int N, H, W, C4, OH, OW, k, s, p;
+  int N, H, W, C4, OH, OW, k, s, p, c4shift;
 };
+
+// K > 0: the window is a compile-time constant (nn.MaxPool2d(3, 2, 1) of the ResNet stem): the loops over the window unroll
+// and the divisions by the stride become shifts -- the generic version spent more time on index arithmetic than on memory
+template <int K, int S, int P>
+__device__ __forceinline__ PoolGeom fixed(PoolGeom g) {
+  if constexpr (K > 0) { g.k = K; g.s = S; g.p = P; }
+  return g;
+}
 
 __device__ __forceinline__ bool takes(float v, float best) { return (v > best) || (v != v); }
 
 // One CTA per output row (n, oh): the W*C4 float4 of up to k input rows are re-read from L1/L2 by neighbouring
 // windows; threads run over (ow, c4) with 32-bit index arithmetic only.
+template <int K, int S, int P, bool POW2>
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
-                                                          uint8_t* __restrict__ idx, const PoolGeom g) {
+                                                          uint8_t* __restrict__ idx, const PoolGeom g0) {
+  const PoolGeom g = fixed<K, S, P>(g0);
   const int n = blockIdx.x / g.OH, oh = blockIdx.x - n * g.OH;
   const int h0 = oh * g.s - g.p;
   const float4* xn = reinterpret_cast<const float4*>(x) + (size_t)n * g.H * g.W * g.C4;
   const size_t obase = ((size_t)n * g.OH + oh) * g.OW * g.C4;
   for (int t = threadIdx.x; t < g.OW * g.C4; t += blockDim.x) {
-    const int ow = t / g.C4, c4 = t - ow * g.C4;
+    const int ow = POW2 ? (t >> g.c4shift) : t / g.C4, c4 = t - ow * g.C4;
     const int w0 = ow * g.s - g.p;
     float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     unsigned bi[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
     for (int kh = 0; kh < g.k; ++kh) {
       const int h = h0 + kh;
       if (h < 0 || h >= g.H) continue;
       const float4* xr = xn + (size_t)h * g.W * g.C4 + c4;
+#pragma unroll
       for (int kw = 0; kw < g.k; ++kw) {
         const int w = w0 + kw;
         if (w < 0 || w >= g.W) continue;
@@ -60,8 +72,10 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restric
 }
 
 // One CTA per input row (n, h): every input float4 gathers from the <= ceil(k/s)^2 windows that contain it.
+template <int K, int S, int P, bool POW2>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx,
-                                                          float* __restrict__ dx, const PoolGeom g) {
+                                                          float* __restrict__ dx, const PoolGeom g0) {
+  const PoolGeom g = fixed<K, S, P>(g0);
   const int n = blockIdx.x / g.H, h = blockIdx.x - n * g.H;
   // windows (oh, ow) with oh*s - p <= h <= oh*s - p + k - 1
   int oh0 = h + g.p - g.k + 1;
@@ -72,7 +86,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
   const uint32_t* ixn = reinterpret_cast<const uint32_t*>(idx) + (size_t)n * g.OH * g.OW * g.C4;
   float4* dxr = reinterpret_cast<float4*>(dx) + ((size_t)n * g.H + h) * g.W * g.C4;
   for (int t = threadIdx.x; t < g.W * g.C4; t += blockDim.x) {
-    const int w = t / g.C4, c4 = t - w * g.C4;
+    const int w = POW2 ? (t >> g.c4shift) : t / g.C4, c4 = t - w * g.C4;
     int ow0 = w + g.p - g.k + 1;
     ow0 = ow0 <= 0 ? 0 : (ow0 + g.s - 1) / g.s;
     int ow1 = (w + g.p) / g.s;
@@ -100,16 +114,28 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
 
 }  // namespace
 
+namespace {
+int pow2_shift(int v) {
+  int sh = 0;
+  while ((1 << sh) < v) ++sh;
+  return (1 << sh) == v ? sh : -1;
+}
+}  // namespace
+
 void maxpool_fwd_launch(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C, int OH, int OW, int k, int s, int p,
                         cudaStream_t st) {
-  const PoolGeom g{N, H, W, C / 4, OH, OW, k, s, p};
-  maxpool_fwd_kernel<<<N * OH, 256, 0, st>>>(x, y, idx, g);
+  const int sh = pow2_shift(C / 4);
+  const PoolGeom g{N, H, W, C / 4, OH, OW, k, s, p, sh < 0 ? 0 : sh};
+  if (k == 3 && s == 2 && p == 1 && sh >= 0) maxpool_fwd_kernel<3, 2, 1, true><<<N * OH, 256, 0, st>>>(x, y, idx, g);
+  else maxpool_fwd_kernel<0, 0, 0, false><<<N * OH, 256, 0, st>>>(x, y, idx, g);
 }
 
 void maxpool_bwd_launch(const float* dy, const uint8_t* idx, float* dx, int N, int H, int W, int C, int OH, int OW, int k, int s,
                         int p, cudaStream_t st) {
-  const PoolGeom g{N, H, W, C / 4, OH, OW, k, s, p};
-  maxpool_bwd_kernel<<<N * H, 256, 0, st>>>(dy, idx, dx, g);
+  const int sh = pow2_shift(C / 4);
+  const PoolGeom g{N, H, W, C / 4, OH, OW, k, s, p, sh < 0 ? 0 : sh};
+  if (k == 3 && s == 2 && p == 1 && sh >= 0) maxpool_bwd_kernel<3, 2, 1, true><<<N * H, 256, 0, st>>>(dy, idx, dx, g);
+  else maxpool_bwd_kernel<0, 0, 0, false><<<N * H, 256, 0, st>>>(dy, idx, dx, g);
 }
 
 }  // namespace dwt

@@ -143,8 +143,12 @@ class Bottleneck(_SiteOwner):
 
 
 class ResNet50DWT(_SiteOwner):
-    def __init__(self, layers, state_dict, num_classes=65, group_size=4, site_mode="modules", stem_pad=0):
+    def __init__(self, layers, state_dict, num_classes=65, group_size=4, site_mode="modules", stem_pad=0, stem_nchw=False):
         super().__init__()
+        # stem_nchw: run ONLY the 3-channel 7x7 stem convolution in NCHW (its weight stays NCHW-contiguous, the image is
+        # viewed / copied to NCHW, the 64-channel result is copied to channels-last once) -- cuDNN's NHWC engines for a
+        # 3-channel input are legacy kernels (profiles/launches_r02_step.md); same arithmetic, different cuDNN kernel
+        self.stem_nchw = stem_nchw
         # stem_pad = 4 / 8: feed the 7x7 stem convolution a zero-padded 4- / 8-channel image and the equally padded
         # weight -- identical arithmetic (the extra products are exact zeros), but cuDNN has no tensor-core kernel for
         # a 3-channel NHWC tensor and falls back to a legacy engine (2.0 ms forward + 2.2 ms weight gradient per
@@ -176,6 +180,8 @@ class ResNet50DWT(_SiteOwner):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
     def _stem(self, x):
+        if self.stem_nchw:
+            return self.conv1(x.contiguous()).contiguous(memory_format=torch.channels_last)
         if not self.stem_pad or x.shape[1] >= self.stem_pad:
             return self.conv1(x)
         extra = self.stem_pad - x.shape[1]
@@ -212,12 +218,14 @@ class ResNet50DWT(_SiteOwner):
         return self.fc_out(torch.flatten(self.avgpool(x), 1))
 
 
-def build_resnet50_dwt(state_dict, layers, site_mode="modules", num_classes=65, channels_last=False, stem_pad=0):
+def build_resnet50_dwt(state_dict, layers, site_mode="modules", num_classes=65, channels_last=False, stem_pad=0,
+                       stem_nchw=False):
     """state_dict uses the reference checkpoint's key names *without* the 7-char
     ``module.`` prefix (resnet50_dwt_mec_officehome.py:370-376).  channels_last=True converts the
     convolution weights to torch.channels_last so that, fed channels-last images, every activation
     stays NHWC (no cuDNN NCHW<->NHWC copies); results are identical, only strides change."""
-    model = ResNet50DWT(layers, state_dict, num_classes=num_classes, site_mode=site_mode, stem_pad=stem_pad)
+    model = ResNet50DWT(layers, state_dict, num_classes=num_classes, site_mode=site_mode, stem_pad=stem_pad,
+                        stem_nchw=stem_nchw and channels_last)
     model.load_state_dict(state_dict, strict=False)
     if channels_last and hasattr(layers, "MaxPool2d"):
         model.maxpool = layers.MaxPool2d(3, stride=2, padding=1)    # the library's channels-last kernel pair (no state)
@@ -225,7 +233,7 @@ def build_resnet50_dwt(state_dict, layers, site_mode="modules", num_classes=65, 
         # only the convolution weights: Module.to(memory_format=...) would also re-stride the [1,C,1,1]
         # running-mean buffers into fresh tensors and silently break the aliasing of the three domain branches
         for m in model.modules():
-            if isinstance(m, nn.Conv2d):
+            if isinstance(m, nn.Conv2d) and not (model.stem_nchw and m is model.conv1):
                 m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
     return model
 
