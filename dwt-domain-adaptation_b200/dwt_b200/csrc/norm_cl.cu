@@ -32,6 +32,8 @@
 // be recomputed without the residual) and bwd_apply also writes the masked gradient for the identity branch.
 //
 // Reference semantics: utils/whitening.py:37-61, utils/batch_norm.py:54-69 (/root/reference).
+#include <stdlib.h>
+
 #include "dwt_common.cuh"
 #include "norm_launch.h"
 #include "small_algebra.cuh"
@@ -40,6 +42,14 @@ namespace dwt {
 namespace {
 
 constexpr int kT = 256;
+
+// Programmatic dependent launch (PDL).  The three launches of a pass form a chain reduction -> finalize -> elementwise.
+// With DWT_PDL=1 the finalize and elementwise kernels are launched with programmaticStreamSerialization: they may become
+// resident while their predecessor is still draining, run their prologue (index arithmetic, parameter loads that do not
+// depend on the predecessor) and block in griddepcontrol.wait until the predecessor grid has completed and flushed.
+// Kernels launched the ordinary way see both instructions as no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <int GS> struct ClShape {
   static constexpr int NSUB = 4 / GS;                       // problems per float4 column
@@ -106,6 +116,7 @@ __global__ void __launch_bounds__(kT, 3) cl_stats_kernel(const float* __restrict
   __shared__ float sRed[kT * S::FWD];
   const ClThread t(gm);
   const unsigned rows = (unsigned)gm.N * gm.HW;
+  pdl_launch_dependents();
   CL_FOR_DOMAINS(d, gm, true) {
     const float* xd = x + (size_t)d * rows * gm.C + 4 * t.q;
     // pilot shift: mean of the first <= 8 rows of the domain, per channel (every thread of a column agrees)
@@ -232,6 +243,8 @@ __global__ void __launch_bounds__(32 * kFinQ * DWT_MAX_DOMAINS) cl_fwd_finalize_
 #pragma unroll
     for (int e = 0; e < GS; ++e) rm_old[e] = fin.rmean[dbuf][g * GS + e];
   }
+  pdl_launch_dependents();
+  pdl_wait();                                       // the reduction's partial rows and pilot shifts are complete
   float a[SH::FWD];
   column_row_sum<SH::FWD>(partial + (size_t)d * nrows * W + (size_t)q * SH::FWD, nrows, W, a);
   if (lead) {
@@ -309,6 +322,7 @@ __global__ void __launch_bounds__(kT, 3) cl_apply_kernel(const float* __restrict
   constexpr int UNROLL = RES ? 4 : 8;
   const ClThread t(gm);
   const unsigned rows = (unsigned)gm.N * gm.HW;
+  pdl_wait();                                       // save_mean / save_w of the finalize launch are complete
   CL_FOR_DOMAINS(d, gm, false) {
     float Wp[S::NSUB][S::NM], bp[S::NSUB][GS];
 #pragma unroll
@@ -377,6 +391,7 @@ __global__ void __launch_bounds__(kT, 2) cl_bwd_reduce_kernel(const float* __res
   __shared__ float sRed[kT * S::BWD];
   const ClThread t(gm);
   const unsigned rows = (unsigned)gm.N * gm.HW;
+  pdl_launch_dependents();
   CL_FOR_DOMAINS(d, gm, true) {
     float Wp[S::NSUB][S::NM], bp[S::NSUB][GS], mu[4];
 #pragma unroll
@@ -455,6 +470,8 @@ __global__ void __launch_bounds__(32 * kFinQ * DWT_MAX_DOMAINS) cl_bwd_finalize_
   using SH = ClShape<GS>;
   const int s = threadIdx.x, d = threadIdx.z, q = blockIdx.x * blockDim.y + threadIdx.y;
   const int W = (gm.C >> 2) * SH::BWD;
+  pdl_launch_dependents();
+  pdl_wait();                                       // the backward reduction's partial rows are complete
   float a[SH::BWD];
   column_row_sum<SH::BWD>(partial + (size_t)d * nrows * W + (size_t)q * SH::BWD, nrows, W, a);
   if (s < SH::NSUB) {                               // lane s finalizes group q * NSUB + s
@@ -495,6 +512,7 @@ __global__ void __launch_bounds__(kT, 2) cl_bwd_apply_kernel(const float* __rest
   constexpr bool RELU = (EPI & DWT_EPI_RELU) != 0 && !MASK;
   const ClThread t(gm);
   const unsigned rows = (unsigned)gm.N * gm.HW;
+  pdl_wait();                                       // the coefficients of the backward finalize launch are complete
   CL_FOR_DOMAINS(d, gm, false) {
     float Wp[S::NSUB][S::NM], bp[S::NSUB][GS], A1[S::NSUB][S::NM], Bm[S::NSUB][S::NM], cv[S::NSUB][GS];
 #pragma unroll
@@ -590,6 +608,23 @@ __global__ void __launch_bounds__(kT, 2) cl_bwd_apply_kernel(const float* __rest
   if ((E_) == 7) { constexpr int kEPI = 7; __VA_ARGS__; }                 \
   else CL_EPI(E_, __VA_ARGS__)
 
+inline bool use_pdl() {
+  static const bool on = [] { const char* v = getenv("DWT_PDL"); return v != nullptr && v[0] == '1'; }();
+  return on;
+}
+
+// ordinary launch, or (pdl) with programmatic stream serialization: see pdl_wait() above
+template <class... KArgs, class... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // grid.x = CTAs sweeping one domain, grid.y = column slabs, grid.z = 1 (domains one after the other) or D
 inline dim3 cl_grid(const Geom& gm, int nctas, int gz) {
   const int C4 = gm.C / 4, CW = C4 < kT ? C4 : kT;
@@ -613,15 +648,16 @@ void cl_stats(const float* x, const Geom& gm, int nctas, int gz, float* partial,
 inline dim3 fin_block(const Geom& gm) { const int c4 = gm.C / 4; return dim3(32, c4 < kFinQ ? c4 : kFinQ, gm.D); }
 void cl_fwd_finalize(const float* partial, int nrows, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st) {
   const dim3 b = fin_block(gm);
-  CL_GS(gm.GS, (cl_fwd_finalize_kernel<kGS><<<(gm.C / 4) / b.y, b, 0, st>>>(partial, nrows, shift, gm, fin)));
+  CL_GS(gm.GS, (launch_k(cl_fwd_finalize_kernel<kGS>, dim3((gm.C / 4) / b.y), b, st, use_pdl(), partial, nrows, shift, gm, fin)));
 }
 void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
               const float* gamma, const float* beta, const float* residual, uint8_t* mask, cudaStream_t st) {
   if (epi == 7) {
-    CL_GS(gm.GS, (cl_apply_kernel<kGS, 7><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, y, gm, mean, w, gamma, beta, residual, mask)));
+    CL_GS(gm.GS, (launch_k(cl_apply_kernel<kGS, 7>, cl_grid(gm, nctas, gz), dim3(kT), st, use_pdl(), x, y, gm, mean, w, gamma, beta, residual, mask)));
     return;
   }
-  CL_GS(gm.GS, CL_EPI(epi, (cl_apply_kernel<kGS, kEPI><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, y, gm, mean, w, gamma, beta, nullptr, nullptr))));
+  CL_GS(gm.GS, CL_EPI(epi, (launch_k(cl_apply_kernel<kGS, kEPI>, cl_grid(gm, nctas, gz), dim3(kT), st, use_pdl(), x, y, gm, mean, w, gamma, beta,
+                                     (const float*)nullptr, (uint8_t*)nullptr))));
 }
 void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
                    const float* gamma, const float* beta, const uint8_t* mask, float* partial, cudaStream_t st) {
@@ -629,12 +665,13 @@ void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas,
 }
 void cl_bwd_finalize(const float* partial, int nrows, const Geom& gm, const BwdFin& fin, cudaStream_t st) {
   const dim3 b = fin_block(gm);
-  CL_GS(gm.GS, (cl_bwd_finalize_kernel<kGS><<<(gm.C / 4) / b.y, b, 0, st>>>(partial, nrows, gm, fin)));
+  CL_GS(gm.GS, (launch_k(cl_bwd_finalize_kernel<kGS>, dim3((gm.C / 4) / b.y), b, st, use_pdl(), partial, nrows, gm, fin)));
 }
 void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, int gz, int epi, const float* coef,
                   const float* mean, const float* w, const float* gamma, const float* beta, const uint8_t* mask, float* dres,
                   cudaStream_t st) {
-  CL_GS(gm.GS, CL_EPI_BWD(epi, (cl_bwd_apply_kernel<kGS, kEPI><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, dout, dx, gm, coef, mean, w, gamma, beta, mask, dres))));
+  CL_GS(gm.GS, CL_EPI_BWD(epi, (launch_k(cl_bwd_apply_kernel<kGS, kEPI>, cl_grid(gm, nctas, gz), dim3(kT), st, use_pdl(), x, dout, dx, gm, coef, mean, w, gamma,
+                                         beta, mask, dres))));
 }
 
 }  // namespace dwt
