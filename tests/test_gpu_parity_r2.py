@@ -369,3 +369,51 @@ def test_maxpool_is_bit_exact_vs_torch(shape, k, s, p, dev):
     from dwt_b200 import _native
     with pytest.raises(_native.NativeError, match="channels_last"):
         dwt_b200.MaxPool2d(k, s, p)(x.contiguous())
+
+
+# --------------------------------------------------------------------------- launch-shape switches (read once per process)
+_SWITCH_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path[:0] = [{plugin!r}, {root!r}]
+import dwt_b200
+from oracle import dwt_oracle as O
+dev = torch.device("cuda", 0)
+rng = np.random.default_rng(7)
+c, hw, nper, gs = 64, 12, 4, 4
+x = rng.standard_normal((3 * nper, c, hw, hw)) * 1.5 + 0.3
+dout = rng.standard_normal(x.shape)
+gamma, beta = 0.5 + rng.random(c), 0.2 * rng.standard_normal(c)
+outs, dxs = [], []
+for d in range(3):
+    xd, dd = x[d * nper:(d + 1) * nper], dout[d * nper:(d + 1) * nper]
+    y, mean, w, *_ = O.whiten_forward(xd, gs)
+    pre = O.scale_shift_relu(y, gamma, beta, False)
+    dz = dd * (pre > 0)
+    dxs.append(O.whiten_backward(xd, dz * gamma.reshape(1, c, 1, 1), mean, w)); outs.append(np.maximum(pre, 0))
+t = lambda a: torch.tensor(a, dtype=torch.float32, device=dev)
+mods = [dwt_b200.WTransform2d(c, gs).to(dev).train() for _ in range(3)]
+xt = t(x).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+g, b = t(gamma.reshape(c, 1, 1)).requires_grad_(True), t(beta.reshape(c, 1, 1)).requires_grad_(True)
+out = dwt_b200.DomainTripleNorm("whiten", c, gs)(xt, mods, g, b, relu=True)
+out.backward(t(dout).contiguous(memory_format=torch.channels_last))
+rel = lambda a, r: float(np.linalg.norm(a - r) / np.linalg.norm(r))
+e = (rel(out.detach().double().cpu().numpy(), np.concatenate(outs)), rel(xt.grad.double().cpu().numpy(), np.concatenate(dxs)))
+assert e[0] < 1e-3 and e[1] < 1e-3, e
+assert dwt_b200._native.status_all(dev) == 0
+print("OK", e)
+"""
+
+
+@pytest.mark.parametrize("env", [{"DWT_CL_SEQ_MB": "0"}, {"DWT_PDL": "1"}, {"DWT_CL_SEQ_MB": "0", "DWT_PDL": "1"}],
+                         ids=["domains_in_sequence", "pdl", "both"])
+def test_channels_last_launch_switches(env, dev):
+    """The experiment switches of the channels-last family -- all CTAs sweeping the domains one after the other
+    (grid.z = 1) and programmatic dependent launch of the finalize / elementwise kernels -- give the same results as the
+    default launch shapes (fused site, forward + backward, against the fp64 oracle).  They are read once per process,
+    hence the subprocess."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = _SWITCH_SCRIPT.format(plugin=os.path.join(root, "dwt-domain-adaptation_b200"), root=root)
+    r = subprocess.run([sys.executable, "-c", script], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
