@@ -4,11 +4,12 @@ The reference runs every norm site as
     split/3 -> bns(x_s) | bnt(x_t) | bnt_aug(x_t') -> cat -> cat -> * gamma + beta -> relu
 (resnet50_dwt_mec_officehome.py:220-222,335-337): three module calls, two full-tensor
 concatenations, an affine pass and a ReLU pass.  ``DomainTripleNorm`` does the whole site in two
-kernel launches (statistics, apply) over the un-split tensor, the three domains batched on
-grid.z, gamma/beta/ReLU folded into the apply pass, and the running-statistic EMA applied
-source -> target -> target-aug in order so aliased buffers end exactly as after three
-sequential module calls.  Backward is likewise two launches and also yields
-dgamma/dbeta.
+tensor-sized kernel launches (statistics, apply; a small finalize launch between them) over the
+un-split tensor, the three domains batched on grid.z, gamma/beta/ReLU (and the Bottleneck's residual
+tail) folded into the apply pass, and the running-statistic EMA applied source -> target ->
+target-aug in order so aliased buffers end exactly as after three sequential module calls
+(SURVEY.md H5).  Backward is likewise two tensor-sized launches and also yields dgamma/dbeta and,
+for the residual tail, the gradient of the identity branch.
 
 It owns no state: it borrows the running buffers of the three domain modules at call time.
 
