@@ -182,10 +182,9 @@ class FlatGradAllReduce:
             off += p.numel()
         # gather = "accumulate": .grad IS the view, autograd adds into it (one small in-place add per parameter and a
         # memset per step); "copy": autograd produces its own gradient tensors, ONE multi-tensor copy moves them into the
-        # flat buffer after backward and .grad is re-pointed at the views for the optimizer (needs segments == 1)
-        if gather == "copy":
-            segments = 1
-        else:
+        # flat buffer and .grad is re-pointed at the views for the optimizer; with segments > 1 the copy and the
+        # collective of a segment are issued from the hook of its last gradient, overlapping the rest of backward
+        if gather != "copy":
             for p, v in zip(params, self.views):
                 p.grad = v
         # segment boundaries in layer order: [stem, layer1, layer2 | layer3 | layer4, fc_out] (fewer when asked)
@@ -201,6 +200,7 @@ class FlatGradAllReduce:
             self.ranges.append((offsets[a], off if b == len(params) else offsets[b], b - a))
             for p in params[a:b]:
                 self.seg_of[id(p)] = k
+        self.seg_items = [(cuts[k], cuts[k + 1]) for k in range(len(cuts) - 1)]      # parameter index range of a segment
         self.pending = [r[2] for r in self.ranges]
         self.works = []
         self.launched = [False] * len(self.ranges)
@@ -212,14 +212,14 @@ class FlatGradAllReduce:
                     p.register_post_accumulate_grad_hook(self._on_grad)
 
     def zero(self):
+        self.pending = [r[2] for r in self.ranges]
+        self.launched = [False] * len(self.ranges)
+        self.works = []
         if self.gather == "copy":
             for p in self.params:
                 p.grad = None
             return
         self.flat.zero_()
-        self.pending = [r[2] for r in self.ranges]
-        self.launched = [False] * len(self.ranges)
-        self.works = []
 
     def _on_grad(self, p):
         k = self.seg_of[id(p)]
@@ -230,6 +230,9 @@ class FlatGradAllReduce:
     def _launch(self, k):
         a, b, _ = self.ranges[k]
         self.launched[k] = True
+        if self.gather == "copy":                    # this segment's gradients -> its piece of the flat buffer
+            i0, i1 = self.seg_items[k]
+            torch._foreach_copy_(self.views[i0:i1], [p.grad for p in self.params[i0:i1]])
         seg = self.flat[a:b]
         if self.flat.is_cuda:
             self.works.append(self.dist.all_reduce(seg, op=self.dist.ReduceOp.AVG, async_op=True))
@@ -237,7 +240,7 @@ class FlatGradAllReduce:
             self.works.append(self.dist.all_reduce(seg, op=self.dist.ReduceOp.SUM, async_op=True))
 
     def reduce(self):
-        if self.gather == "copy":
+        if self.gather == "copy" and (len(self.ranges) == 1 or self.world <= 1):
             torch._foreach_copy_(self.views, [p.grad for p in self.params])
             for p, v in zip(self.params, self.views):
                 p.grad = v
@@ -257,6 +260,9 @@ class FlatGradAllReduce:
             w.wait()                                 # CUDA: the compute stream waits on NCCL's stream, the host does not
         if not self.flat.is_cuda:
             self.flat.div_(self.world)
+        if self.gather == "copy":
+            for p, v in zip(self.params, self.views):
+                p.grad = v
 
 
 def train_step(model, mec, opt, images, labels, sync=None, head=None):
@@ -368,8 +374,6 @@ def workload_config(args, per_domain):
 
 def implementation_note(args):
     seg = getattr(args, "grad_segments", 1)
-    if getattr(args, "grad_gather", "accumulate") == "copy":
-        seg = 1
     return {"site_mode": args.site_mode, "memory_format": args.memory_format,
             "launch": "CUDA-graph replay of the whole step" if args.cuda_graph else "eager",
             "grad_gather": getattr(args, "grad_gather", "accumulate"),

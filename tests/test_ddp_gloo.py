@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PICK = ["conv1.weight", "gamma1", "layer1.0.beta2", "layer2.1.gamma3", "layer4.2.conv3.weight", "fc_out.bias"]
 
 
-def _step(rank_seed, ddp, gather="accumulate"):
+def _step(rank_seed, ddp, gather="accumulate", segments=3):
     sys.path[:0] = [ROOT]
     import bench
     import oracle.torch_port as port
@@ -27,7 +27,7 @@ def _step(rank_seed, ddp, gather="accumulate"):
     torch.manual_seed(0)
     torch.set_num_threads(2)
     model = bench.build_model(port, torch.device("cpu"), "modules")
-    sync = bench.FlatGradAllReduce(model, 2, gather=gather) if ddp else None      # the data-parallel plumbing of bench.py
+    sync = bench.FlatGradAllReduce(model, 2, segments=segments, gather=gather) if ddp else None   # the data-parallel plumbing of bench.py
     opt = torch.optim.SGD(model.parameters(), lr=0.0)               # lr 0: inspect the synchronised gradients
     mec = port.MinEntropyConsensusLoss(bench.NUM_CLASSES, "cpu")
     images, labels = synth_batch(seed=rank_seed, per_domain=1, size=64)
@@ -36,21 +36,21 @@ def _step(rank_seed, ddp, gather="accumulate"):
     return {k: params[k].grad.clone() for k in PICK}, model.state_dict()["bns1.wh.running_mean"].clone()
 
 
-def _worker(rank, world, port_no, out_dir, gather):
+def _worker(rank, world, port_no, out_dir, gather, segments):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port_no}", rank=rank, world_size=world)
-    grads, buf = _step(100 + rank, ddp=True, gather=gather)
+    grads, buf = _step(100 + rank, ddp=True, gather=gather, segments=segments)
     torch.save({"grads": grads, "buf": buf}, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("gather", ["accumulate", "copy"])          # 3 overlapped segments / one multi-tensor copy + 1 collective
-def test_two_rank_step_averages_gradients_and_keeps_statistics_local(tmp_path, gather):
+@pytest.mark.parametrize("gather,segments", [("accumulate", 3), ("copy", 1), ("copy", 3)])   # overlapped segments / one copy + one collective / both
+def test_two_rank_step_averages_gradients_and_keeps_statistics_local(tmp_path, gather, segments):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port_no = s.getsockname()[1]
-    mp.spawn(_worker, args=(2, port_no, str(tmp_path), gather), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port_no, str(tmp_path), gather, segments), nprocs=2, join=True)
     r0, r1 = (torch.load(tmp_path / f"rank{r}.pt") for r in range(2))
     g0, b0 = _step(100, ddp=False)
     g1, b1 = _step(101, ddp=False)
