@@ -28,7 +28,8 @@
 // comes out of ONE M=128 N=80 K=8 MMA per 8 pixels: the A operand [hi ; lo] (128 rows: TMEM lanes 0..63 = hi of channels
 // 0..63, lanes 64..127 = their lo) is written to TENSOR MEMORY by the transform warps (tcgen05.st, lane = row; a warp
 // may only touch its own 32-lane quarter, so warps are hi warps or lo warps), the B operand is the hi tile written
-// back in place plus 16 constant rows (a row of ones: accumulator column 64 = the row sums the mean needs).
+// back in place plus 16 constant rows (a row of ones: accumulator column 64 = the row sums the mean needs).  Tiles
+// alternate between two accumulators so that two dependent tcgen05.mma chains are in flight per CTA.
 // hi = RN_tf32(s), lo = s - hi.  Measured on B200 (tests/test_gpu_parity_r2.py): covariance error 6e-8 (single tf32
 // pass: 4e-6), y error at cond 1e3 / 1e4 3.6e-6 / 2.3e-5 (single pass 1.2e-4 / 2.9e-4, the fp32 reference itself
 // 3.2e-5 / 2.1e-4).
@@ -58,7 +59,10 @@ constexpr int kStagesStats = 12, kStagesBwd = 6;      // 97 KB per CTA, two CTAs
 constexpr int kTmemCols = 64;
 // split-precision Gram kernel: accumulator (80 columns, padded to 96) + a ring of A-operand slots (32 columns =
 // 32 pixels each); two CTAs per SM share the 512 columns of tensor memory
-constexpr int kGramASlots = 5, kGramTmemCols = 256;
+// kGramAcc independent accumulators (tiles alternate between them): consecutive tcgen05.mma into ONE accumulator form a
+// dependent chain -- the round-1 single-pass kernel and the first split kernels, very different otherwise, both ran at
+// ~270 cycles per MMA per CTA -- and two chains overlap their latency.  80 columns each, then the A slots.
+constexpr int kGramAcc = 2, kGramASlots = 3, kGramTmemCols = 256;
 
 // ------------------------------------------------------------------------------------------
 // shared memory carve-up
@@ -69,6 +73,7 @@ struct TcBarriers {
   uint64_t empty[kStagesStats];
   uint64_t a_empty[kGramASlots];     // Gram kernel: the MMAs that read tensor-memory A slot a have completed
   uint64_t accum;
+  uint64_t accum2;                   // Gram kernel: second MMA issuer's accumulator is complete
   uint32_t tmem_slot;
   int flag;
 };
@@ -171,7 +176,7 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     if (lane == 0) {
       for (int it = 0; it < ntiles; ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
-        mbar_wait(&bars.empty[s], ph ^ 1);
+        mbar_wait_relaxed(&bars.empty[s], ph ^ 1);
         const int t = tr.begin + it, n = t / tr.PB, pb = t - n * tr.PB;
         uint8_t* dst = smem + (size_t)s * NT * kTileBytes;
         mbar_arrive_expect_tx(&bars.full[s], NT * kTileBytes);
@@ -327,10 +332,16 @@ struct RingPos {
   __device__ __forceinline__ void advance(int step, int n) { i += step; if (i >= n) { i -= n; phase ^= 1; } }
 };
 
-__global__ void __launch_bounds__(kTcThreads, 2)
+// 11 warps: TMA producer, MMA issuer 0, 8 transform warps, MMA issuer 1 (tiles alternate between the two issuers, each
+// with its own accumulator).  One thread issuing the 4 tcgen05.mma + 2 tcgen05.commit of EVERY tile was the bottleneck of
+// the single-issuer versions (~1000 cycles per tile whatever the number of accumulators or A slots; the same 4 MMAs per
+// tile paced the round-1 single-pass kernel) -- profiles/ncu_r02_tc_gram.md.
+constexpr int kGramThreads = kTcThreads + 32;
+
+__global__ void __launch_bounds__(kGramThreads, 2)
 tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restrict__ x, const Geom gm,
                float* __restrict__ shift_out, float* __restrict__ partial) {
-  constexpr int STAGES = kGramStages, NA = kGramASlots;    // A slots behind the 96 accumulator columns: 96 + 5*32 = 256
+  constexpr int STAGES = kGramStages, NA = kGramASlots, NACCUM = kGramAcc;    // 2 x 80 accumulator columns + 3 x 32 = 256
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ TcBarriers bars;
@@ -345,6 +356,7 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.ready[s], 4); mbar_init(&bars.empty[s], 1); }
     for (int a = 0; a < NA; ++a) mbar_init(&bars.a_empty[a], 1);
     mbar_init(&bars.accum, 1);
+    mbar_init(&bars.accum2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<kGramTmemCols>(&bars.tmem_slot);
@@ -362,7 +374,7 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
     if (blockIdx.x == 0) shift_out[((size_t)d * gridDim.y + sb) * kTileCh + r] = sh;
   }
   // constant rows 64..79 of every stage (128 16-byte chunks each): row 64 (chunks 0..7, un-swizzled: 64 & 7 == 0) = 1.0
-  for (int e = tid; e < STAGES * 128; e += kTcThreads) {
+  for (int e = tid; e < STAGES * 128; e += kGramThreads) {
     const int s = e >> 7, q = e & 127;
     const float val = q < 8 ? 1.f : 0.f;
     sts128(smem_u32(smem + (size_t)s * kGramStageBytes + kTileBytes) + 16u * (uint32_t)q, val, val, val, val);
@@ -372,7 +384,7 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_slot;
-  const uint32_t tmem_d = tmem, tmem_a0 = tmem + 96;            // accumulator: columns 0..79; A slots from column 96
+  const uint32_t tmem_d = tmem, tmem_a0 = tmem + NACCUM * kGramN;   // accumulators: columns 0..159; A slots from column 160
 
   // transform-warp geometry: two sets of four warps take alternate tiles; a warp may only touch the TMEM quarter
   // warp & 3: quarters 0, 1 = hi rows of channels 0..63 (lane = channel), quarters 2, 3 = their lo rows
@@ -386,31 +398,35 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
       RingPos st(0, STAGES);
       int n = tr.begin / tr.PB, pb = tr.begin - n * tr.PB;
       for (int it = 0; it < ntiles; ++it) {
-        mbar_wait(&bars.empty[st.i], st.phase ^ 1);
+        mbar_wait_relaxed(&bars.empty[st.i], st.phase ^ 1);
         mbar_arrive_expect_tx(&bars.full[st.i], kTileBytes);
         tma_load_3d(smem + (size_t)st.i * kGramStageBytes, &map_x, pb * kTilePx, ch0, d * gm.N + n, &bars.full[st.i]);
         st.advance(1, STAGES);
         if (++pb == tr.PB) { pb = 0; ++n; }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer: D[128 x 80] += [hi ; lo] (tensor memory) x [hi tile ; ones ; 0]^T (shared memory) =====
+  } else if (warp == 1 || warp == 10) {
+    // ===== MMA issuers: D_m[128 x 80] += [hi ; lo] (tensor memory) x [hi tile ; ones ; 0]^T (shared memory) =====
+    // issuer m takes tiles m, m + 2, ... into accumulator m
     constexpr uint32_t idesc = make_idesc_tf32(128, kGramN);
-    RingPos st(0, STAGES), as(0, NA);
-    for (int it = 0; it < ntiles; ++it) {
+    const int m = warp == 1 ? 0 : 1;
+    RingPos st(m, STAGES), as(m, NA);
+    const uint32_t dacc = tmem_d + (uint32_t)(m * kGramN);
+    const int last = ntiles - 1 - ((ntiles - 1 - m) & 1);       // last tile of this issuer's parity (< m: none)
+    for (int it = m; it < ntiles; it += 2) {
       mbar_wait(&bars.ready[st.i], st.phase);
       tc_fence_after();
       if (lane == 0) {
         const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + (size_t)st.i * kGramStageBytes));
 #pragma unroll
         for (int k = 0; k < kTilePx / 8; ++k)
-          umma_tf32_ts(tmem_d, tmem_a0 + (uint32_t)(as.i * kTilePx + 8 * k), bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_tf32_ts(dacc, tmem_a0 + (uint32_t)(as.i * kTilePx + 8 * k), bdesc + 2 * k, idesc, (it >= 2 || k > 0) ? 1u : 0u);
         umma_commit(&bars.empty[st.i]);
         umma_commit(&bars.a_empty[as.i]);
-        if (it == ntiles - 1) umma_commit(&bars.accum);
+        if (it == last) umma_commit(m == 0 ? &bars.accum : &bars.accum2);
       }
       __syncwarp();
-      st.advance(1, STAGES); as.advance(1, NA);
+      st.advance(2, STAGES); as.advance(2, NA);
     }
   } else {
     // ===== transform warps =====
@@ -446,11 +462,26 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
   const bool epi_warp = warp >= 2 && warp < 6;     // one warp per TMEM quarter
   if (epi_warp && ntiles > 0) {
     mbar_wait(&bars.accum, 0);
+    if (ntiles > 1) mbar_wait(&bars.accum2, 0);
     tc_fence_after();
     float tail[16];
     tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16), reinterpret_cast<float(&)[32]>(P[0]));
     tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + 32, reinterpret_cast<float(&)[32]>(P[32]));
     tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + 64, tail);
+#pragma unroll
+    for (int acc = 1; acc < NACCUM; ++acc) {
+      if (acc < ntiles) {                           // accumulator `acc` received tiles acc, acc + NACCUM, ...
+        float t32[32], t16[16];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kGramN + half * 32), t32);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) P[half * 32 + j] += t32[j];
+        }
+        tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kGramN + 64), t16);
+        tail[0] += t16[0];
+      }
+    }
     tc_fence_before();
     rs = tail[0];                                  // sum over the CTA's samples of hi (hi rows) / lo (lo rows)
     if (lo_warp) {
@@ -537,7 +568,7 @@ int tc_stats(const float* x, const Geom& gm, int nchunks, float* shift, float* p
   bind_context();
   if (int rc = make_map(&mx, x, gm)) return rc;
   dim3 grid(nchunks, tc_superblocks(gm), gm.D);
-  tc_gram_kernel<<<grid, kTcThreads, tc_smem_bytes(false), st>>>(mx, x, gm, shift, partial);
+  tc_gram_kernel<<<grid, kGramThreads, tc_smem_bytes(false), st>>>(mx, x, gm, shift, partial);
   return 0;
 }
 
