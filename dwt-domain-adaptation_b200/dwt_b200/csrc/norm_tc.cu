@@ -71,9 +71,7 @@ struct TcBarriers {
   uint64_t full[kStagesStats];
   uint64_t ready[kStagesStats];
   uint64_t empty[kStagesStats];
-  uint64_t a_empty[kGramASlots];     // Gram kernel: the MMAs that read tensor-memory A slot a have completed
   uint64_t accum;
-  uint64_t accum2;                   // Gram kernel: second MMA issuer's accumulator is complete
   uint32_t tmem_slot;
   int flag;
 };
@@ -325,11 +323,19 @@ constexpr int kGramN = kTileCh + 16;
 constexpr int kGramStageBytes = kGramN * kTilePx * 4;            // 10240
 constexpr int kGramStages = 9;                                   // 90 KB + alignment: two CTAs per SM
 
-// ring position (stage or A slot) advanced by a fixed step without divisions
-struct RingPos {
-  int i, phase;
-  __device__ __forceinline__ RingPos(int start, int n) : i(start % n), phase((start / n) & 1) {}
-  __device__ __forceinline__ void advance(int step, int n) { i += step; if (i >= n) { i -= n; phase ^= 1; } }
+// Barriers of the Gram kernel.  Tiles alternate between two transform sets and two MMA issuers while the data rings
+// (9 stages, 3 A slots) have ODD lengths, so consecutive uses of one stage / slot belong to different waiters -- and an
+// mbarrier parity wait is only sound for a waiter that is at most one phase away from the barrier (two phases off it
+// falls through).  Every (ring index, tile parity) pair therefore has its own barrier: barrier rings of twice the
+// data-ring length, indexed by tile mod 2L with phase (tile / 2L) & 1.  All phases of one barrier then belong to one
+// waiter, which visits them in order, and nothing depends on how far the warps drift apart.
+struct GramBarriers {
+  uint64_t full[2 * kGramStages];      // TMA landed tile t                          waiter: transform set t & 1
+  uint64_t ready[2 * kGramStages];     // the 4 warps of set t & 1 transformed t      waiter: MMA issuer t & 1
+  uint64_t empty[kGramStages];         // MMAs of tile t complete, stage free         waiter: the producer, every phase
+  uint64_t a_empty[2 * kGramASlots];   // MMAs of tile t complete, A slot free        waiter: set (t + 3) & 1
+  uint64_t accum[kGramAcc];            // issuer m's accumulator is final
+  uint32_t tmem_slot;
 };
 
 // 11 warps: TMA producer, MMA issuer 0, 8 transform warps, MMA issuer 1 (tiles alternate between the two issuers, each
@@ -344,7 +350,7 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
   constexpr int STAGES = kGramStages, NA = kGramASlots, NACCUM = kGramAcc;    // 2 x 80 accumulator columns + 3 x 32 = 256
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ TcBarriers bars;
+  __shared__ GramBarriers bars;
   __shared__ float sShift[kTileCh];
   __shared__ float sRS[kTileCh];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
@@ -353,10 +359,10 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
   const int ntiles = tr.end - tr.begin;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.ready[s], 4); mbar_init(&bars.empty[s], 1); }
-    for (int a = 0; a < NA; ++a) mbar_init(&bars.a_empty[a], 1);
-    mbar_init(&bars.accum, 1);
-    mbar_init(&bars.accum2, 1);
+    for (int s = 0; s < 2 * STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.ready[s], 4); }
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars.empty[s], 1);
+    for (int a = 0; a < 2 * NA; ++a) mbar_init(&bars.a_empty[a], 1);
+    for (int m = 0; m < NACCUM; ++m) mbar_init(&bars.accum[m], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<kGramTmemCols>(&bars.tmem_slot);
@@ -395,60 +401,57 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      RingPos st(0, STAGES);
       int n = tr.begin / tr.PB, pb = tr.begin - n * tr.PB;
       for (int it = 0; it < ntiles; ++it) {
-        mbar_wait_relaxed(&bars.empty[st.i], st.phase ^ 1);
-        mbar_arrive_expect_tx(&bars.full[st.i], kTileBytes);
-        tma_load_3d(smem + (size_t)st.i * kGramStageBytes, &map_x, pb * kTilePx, ch0, d * gm.N + n, &bars.full[st.i]);
-        st.advance(1, STAGES);
+        const int s = it % STAGES;
+        uint64_t* full = &bars.full[it % (2 * STAGES)];
+        mbar_wait_relaxed(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(full, kTileBytes);
+        tma_load_3d(smem + (size_t)s * kGramStageBytes, &map_x, pb * kTilePx, ch0, d * gm.N + n, full);
         if (++pb == tr.PB) { pb = 0; ++n; }
       }
     }
   } else if (warp == 1 || warp == 10) {
     // ===== MMA issuers: D_m[128 x 80] += [hi ; lo] (tensor memory) x [hi tile ; ones ; 0]^T (shared memory) =====
-    // issuer m takes tiles m, m + 2, ... into accumulator m
+    // issuer m takes tiles m, m + 2, ... into accumulator m (GramBarriers: its `ready` barriers are its own)
     constexpr uint32_t idesc = make_idesc_tf32(128, kGramN);
     const int m = warp == 1 ? 0 : 1;
-    RingPos st(m, STAGES), as(m, NA);
     const uint32_t dacc = tmem_d + (uint32_t)(m * kGramN);
-    const int last = ntiles - 1 - ((ntiles - 1 - m) & 1);       // last tile of this issuer's parity (< m: none)
     for (int it = m; it < ntiles; it += 2) {
-      mbar_wait(&bars.ready[st.i], st.phase);
+      mbar_wait(&bars.ready[it % (2 * STAGES)], (it / (2 * STAGES)) & 1);
       tc_fence_after();
       if (lane == 0) {
-        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + (size_t)st.i * kGramStageBytes));
+        const int s = it % STAGES, a = it % NA;
+        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + (size_t)s * kGramStageBytes));
 #pragma unroll
         for (int k = 0; k < kTilePx / 8; ++k)
-          umma_tf32_ts(dacc, tmem_a0 + (uint32_t)(as.i * kTilePx + 8 * k), bdesc + 2 * k, idesc, (it >= 2 || k > 0) ? 1u : 0u);
-        umma_commit(&bars.empty[st.i]);
-        umma_commit(&bars.a_empty[as.i]);
-        if (it == last) umma_commit(m == 0 ? &bars.accum : &bars.accum2);
+          umma_tf32_ts(dacc, tmem_a0 + (uint32_t)(a * kTilePx + 8 * k), bdesc + 2 * k, idesc, (it >= 2 || k > 0) ? 1u : 0u);
+        umma_commit(&bars.empty[s]);
+        umma_commit(&bars.a_empty[it % (2 * NA)]);
+        if (it + 2 >= ntiles) umma_commit(&bars.accum[m]);
       }
       __syncwarp();
-      st.advance(2, STAGES); as.advance(2, NA);
     }
   } else {
     // ===== transform warps =====
     const float shift = sShift[row];
     const bool rowok = (ch0 + row) < gm.C;
     const uint32_t smem0 = smem_u32(smem), ta0 = tmem_a0 + ((uint32_t)(quad * 32) << 16);
-    RingPos st(set, STAGES), as(set, NA);
     const int pair_bar = 1 + 2 * set + (quad & 1);       // hi warp (quarter q) and lo warp (quarter q + 2) of the same rows
     const int t0 = tr.begin + set;
     int n = t0 / tr.PB, pb = t0 - n * tr.PB;
     for (int it = set; it < ntiles; it += 2) {
-      mbar_wait(&bars.full[st.i], st.phase);
-      mbar_wait(&bars.a_empty[as.i], as.phase ^ 1);
+      const int s = it % STAGES, a = it % NA, u = it - NA;                // u: the tile that used A slot a before
+      mbar_wait(&bars.full[it % (2 * STAGES)], (it / (2 * STAGES)) & 1);
+      if (u >= 0) mbar_wait(&bars.a_empty[u % (2 * NA)], (u / (2 * NA)) & 1);
       tc_fence_after();
-      const uint32_t tile = smem0 + (uint32_t)(st.i * kGramStageBytes), ta = ta0 + (uint32_t)(as.i * kTilePx);
+      const uint32_t tile = smem0 + (uint32_t)(s * kGramStageBytes), ta = ta0 + (uint32_t)(a * kTilePx);
       if (lo_warp) gram_transform_row<true>(tile, row, shift, pb * kTilePx, gm.HW, rowok, ta, pair_bar);
       else gram_transform_row<false>(tile, row, shift, pb * kTilePx, gm.HW, rowok, ta, pair_bar);
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.ready[st.i]);
-      st.advance(2, STAGES); as.advance(2, NA);
+      if (lane == 0) mbar_arrive(&bars.ready[it % (2 * STAGES)]);
       pb += 2;
       while (pb >= tr.PB) { pb -= tr.PB; ++n; }
     }
@@ -461,8 +464,8 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
   float P[kTileCh], rs = 0.f;
   const bool epi_warp = warp >= 2 && warp < 6;     // one warp per TMEM quarter
   if (epi_warp && ntiles > 0) {
-    mbar_wait(&bars.accum, 0);
-    if (ntiles > 1) mbar_wait(&bars.accum2, 0);
+    mbar_wait(&bars.accum[0], 0);
+    if (ntiles > 1) mbar_wait(&bars.accum[1], 0);
     tc_fence_after();
     float tail[16];
     tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16), reinterpret_cast<float(&)[32]>(P[0]));

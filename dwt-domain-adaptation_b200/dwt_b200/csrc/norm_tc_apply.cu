@@ -16,12 +16,11 @@
 //           written per element;
 //   centring is linear, M (x - shift) = M x - M shift, and is applied as one constant per row at the end.
 //
-// CTA = 2 + 8 + 8 + 1 warps, one per SM, persistent over a contiguous range of 128-pixel tiles of one (domain,
+// CTA = 2 + 8 + 8 warps, one per SM, persistent over a contiguous range of 128-pixel tiles of one (domain,
 // super-block); every input tensor of a tile is one STEP through the rings:
 //   warp 0     TMA producer into a RAW ring (4 boxes of 32 px x 64 ch per slot,
 //              SWIZZLE_128B_ATOM_32B: the only layout the tensor core takes for an MN-major tf32 operand)
-//   warp 1, 18 MMA issuers, alternating tiles (tcgen05.mma kind::tf32, M=128 N=128 K=8; A resident in TMEM, B MN-major);
-//              warp 1 owns the TMEM allocation
+//   warp 1     MMA issuer (tcgen05.mma kind::tf32, M=128 N=128 K=8; A resident in TMEM, B MN-major), TMEM owner
 //   TW warps   transform: raw slot -> lo slot
 //   EW warps   epilogue: tcgen05.ld of this warp's lane quadrant x 64 columns, hi/lo row halves folded by a
 //              half-warp exchange in which each half keeps 32 columns (one full 128-byte line per lane), 256-bit stores.
@@ -29,8 +28,14 @@
 //              epilogue into one chain: 1.5 us per two-input tile against 0.6 us of tensor time.)
 // The raw ring is deeper than the lo ring: a raw slot is busy from the TMA issue to the end of its MMAs (one HBM
 // latency + transform + MMA), a lo slot only from the transform to the end of the MMAs, and the bytes in flight
-// from HBM -- what bounds this kernel -- are the raw slots alone.  Three TMEM accumulators are in flight (three
-// independent tcgen05.mma dependency chains).
+// from HBM -- what bounds this kernel -- are the raw slots alone.  TMEM accumulators are double-buffered.
+//
+// Round 2: a third accumulator changed nothing (292 / 443 us against 290-296 / 435-456 us).  A second MMA-issuing warp
+// (alternate tiles; the one thread issuing 16 / 32 tcgen05.mma + 3 / 5 tcgen05.commit per tile is ~4100 cycles per
+// two-input tile against 4150 at the HBM rate) needs per-issuer lo rings and accumulators: with the shared 2-slot lo
+// ring an issuer that skips the other's tiles meets mbarrier phases two steps away from its own count (parity waits are
+// only meaningful one phase away) -- it faulted on the full-size tensor and was backed out; the Gram kernel, whose
+// rings are deep, runs with two issuers (norm_tc.cu).
 //
 // Measured ceilings on B200 (N=256, C=256, 56x56, profiles/tc_apply_experiments_r01.md): TMA loads alone 0.96 of
 // the HBM peak; a pure TMA load->store copy in this tile order 0.88-0.91.
@@ -64,20 +69,17 @@ template <int NIN> struct ApCfg {
   static constexpr int NBOX = TPX / kBoxPx;
   static constexpr int TW = 8;                         // transform warps
   static constexpr int EW = 8;                         // epilogue warps
-  static constexpr int THREADS = 64 + 32 * (TW + EW) + 32;   // TMA, MMA issuer 0, transform, epilogue, MMA issuer 1
+  static constexpr int THREADS = 64 + 32 * (TW + EW);
   static constexpr int RAW = 5;
   static constexpr int SLOT = NBOX * kBoxBytes;
-  static constexpr int NACC = 3;                       // accumulators in flight: the 16 / 32 tcgen05.mma of a tile form ONE dependent
-                                                       // chain (~270 cycles per link); with two chains the two-input kernel was bound by
-                                                       // them (32 x 270 / 2 = 4300 cycles per tile against 4150 at the HBM rate)
-  static constexpr int TMEM = 512;                     // NACC accumulators of TPX columns + NIN matrices of 64 (3*128 + 2*64 = 512)
+  static constexpr int TMEM = 512;                     // 2 accumulators of TPX columns + NIN matrices of 64
   static constexpr size_t SMEM = (size_t)(RAW + kLo) * SLOT + 1024;
 };
 
 struct ApBarriers {
   uint64_t full[kMaxRaw], raw_empty[kMaxRaw];       // TMA landed / MMAs done with the raw slot
   uint64_t ready[kLo], lo_empty[kLo];               // lo slot written / MMAs done with it
-  uint64_t acc_full[3], acc_empty[3];
+  uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_slot;
 };
 
@@ -146,7 +148,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   if (tid == 0) {
     for (int r = 0; r < RAW; ++r) { mbar_init(&bars.full[r], 1); mbar_init(&bars.raw_empty[r], 1); }
     for (int l = 0; l < kLo; ++l) { mbar_init(&bars.ready[l], TW); mbar_init(&bars.lo_empty[l], 1); }
-    for (int b = 0; b < Cfg::NACC; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_empty[b], EW); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_empty[b], EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM>(&bars.tmem_slot);
@@ -158,7 +160,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_slot;
-  const uint32_t tmem_acc = tmem, tmem_mat = tmem + Cfg::NACC * TPX;
+  const uint32_t tmem_acc = tmem, tmem_mat = tmem + 2 * TPX;
 
   if (warp >= 2 + TW && warp < 6 + TW) {
     // four of the epilogue warps first park the split matrices in tensor memory and form the row constants
@@ -208,12 +210,11 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1 || warp == 2 + TW + EW) {
-    // ===== MMA issuers: tiles alternate between two issuing warps (one thread issuing the 16 / 32 tcgen05.mma and
-    // 3 / 5 tcgen05.commit of every tile was ~4100 cycles per two-input tile against 4150 at the HBM rate) =====
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc_tf32(128, TPX, true);
-    for (int it = (warp == 1 ? 0 : 1); it < ntiles; it += 2) {
-      const int b = it % Cfg::NACC, aph = (it / Cfg::NACC) & 1;
+    for (int it = 0; it < ntiles; ++it) {
+      const int b = it & 1, aph = (it >> 1) & 1;
       mbar_wait(&bars.acc_empty[b], aph ^ 1);
 #pragma unroll
       for (int i = 0; i < NIN; ++i) {
@@ -264,7 +265,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     const int ch = ch0 + 16 * quad + (lane & 15);
     const float rconst = sConst[16 * quad + (lane & 15)];   // sum_i (M_i shift_i)[row]: the centring, applied at the end
     for (int e = 0; e < ntiles; ++e) {
-      const int b = e % Cfg::NACC, aph = (e / Cfg::NACC) & 1;
+      const int b = e & 1, aph = (e >> 1) & 1;
       mbar_wait(&bars.acc_full[b], aph);
       tc_fence_after();
       float v[WC];

@@ -110,6 +110,32 @@ def test_tensor_core_path_all_modes(case, dev):
     assert _native.status(dev) == 0
 
 
+@pytest.mark.parametrize("case", [(64, 256, 28, 28, 64), (6, 128, 28, 28, 64), (5, 64, 30, 30, 8)],
+                         ids=lambda c: "n{}c{}h{}w{}g{}".format(*c))
+def test_tensor_core_path_is_run_to_run_identical(case, dev):
+    """The TMA / transform / tcgen05 pipelines (two transform sets, two MMA issuers, ring barriers) hold no atomics and
+    reduce their partials in a fixed order: 40 repetitions of forward + backward on one input must agree BIT FOR BIT --
+    a stage or tensor-memory slot overwritten before its reader is done shows up here as a run that differs."""
+    import whitening
+    nimg, c, h, w, gs = case
+    gen = torch.Generator(device=dev).manual_seed(7)
+    x = (torch.randn(nimg, c, h, w, device=dev, generator=gen) * 1.5 + 0.7).requires_grad_(True)
+    dy = torch.randn(nimg, c, h, w, device=dev, generator=gen)
+    first = None
+    for rep in range(40):
+        m = whitening.WTransform2d(c, gs).to(dev).train()
+        y = m(x)
+        (dx,) = torch.autograd.grad(y, x, dy)
+        got = (y.detach(), dx, m.running_mean.clone(), m.running_variance.clone())
+        if first is None:
+            first = [g.clone() for g in got]
+            continue
+        for name, a, b in zip(("y", "dx", "running_mean", "running_variance"), got, first):
+            assert torch.equal(a, b), (name, rep, (a - b).abs().max().item())
+    from dwt_b200 import _native
+    assert _native.status(dev) == 0
+
+
 def _conditioned(rng, nimg, c, h, w, gs, cond, scale, mean_over_sigma=0.0):
     """Channels whose per-group covariance has eigenvalues scale^2 * logspace(0, -log10(cond)) in a random
     orthogonal basis, plus a per-channel mean of mean_over_sigma standard deviations."""

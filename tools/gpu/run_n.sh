@@ -1,7 +1,7 @@
 #!/bin/bash
-# round-2 GPU call N (1 GPU): tc_gram with two accumulators (two dependent MMA chains per CTA), 3 A slots
+# round-2 GPU call N (1 GPU): tc_gram with per-parity barrier rings; TC tests, microbench x2, ncu of tc_gram
 mkdir -p gpurun_out/n
-timeout 600 python -m pytest tests/test_gpu_parity_r2.py tests/test_gpu_parity.py -m gpu -q -s -p no:cacheprovider -k "tensor_core or non_pd or whitening_vs or microbench_shape or fused_triple or graph_capturable" > gpurun_out/n/pytest_tc.log 2>&1; echo "pytest tc rc=$?"
+timeout 600 python -m pytest tests/test_gpu_parity_r2.py tests/test_gpu_parity.py -m gpu -q -s -p no:cacheprovider -k "tensor_core or run_to_run or non_pd or whitening_vs or microbench_shape or fused_triple or graph_capturable" > gpurun_out/n/pytest_tc.log 2>&1; echo "pytest tc rc=$?"
 grep -E "passed|failed|error" gpurun_out/n/pytest_tc.log | tail -3
 for i in 1 2; do
 timeout 600 python bench.py --workload microbench --no-cpu-baseline > gpurun_out/n/micro$i.json 2> gpurun_out/n/micro$i.err; echo "micro rc=$?"
