@@ -9,6 +9,7 @@ but travels to the GPU box with the gpurun snapshot.
 from __future__ import annotations
 
 import os
+import shlex
 import subprocess
 import sys
 
@@ -18,6 +19,7 @@ LIB = os.path.join(HERE, "lib", "libdwt_b200.so")
 SOURCES = ["api.cu", "norm_small.cu", "norm_tiled.cu", "norm_tc.cu", "norm_tc_apply.cu", "norm_dense.cu", "norm_cl.cu", "mec.cu", "augment.cu", "pool.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
+NVCC_FLAGS += shlex.split(os.environ.get("DWT_NVCC_EXTRA", ""))     # development only, e.g. -DDWT_PROF_DENSE (phase clocks)
 
 
 def _nvcc() -> str:

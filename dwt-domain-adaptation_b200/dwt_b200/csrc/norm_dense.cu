@@ -9,11 +9,14 @@
 //   bwd_coef         per (domain, group): A1 = W^T, Bm = (2a/M) sym(W^T Phi(-R W^T) W), cvec
 //
 // All three keep a 64x64 problem in ONE 256-thread CTA arranged 16x16, each thread owning a 4x4
-// register block (the whole matrix lives in registers during the factorisation; shared memory only
-// carries the broadcast column / operand panels), so the 64 sequential Cholesky steps cost two
-// barriers and ~20 FMAs each instead of a shared-memory round trip per element.
+// register block.  fwd_factor runs the Cholesky factorisation AND the triangular inverse as one blocked
+// right-looking sweep of 16 panel steps (one block barrier each): the matrices live in registers, shared
+// memory only carries the 4-column panel of L and the 4-row panel of W of the current step.
 //
 // Reference: utils/whitening.py:47-53,57-59 (/root/reference); backward: SURVEY.md §8a.
+#ifdef DWT_PROF_DENSE
+#include <cstdio>
+#endif
 #include "dwt_common.cuh"
 #include "norm_launch.h"
 
@@ -24,6 +27,21 @@ constexpr int kSB = 64;                         // super-block edge
 constexpr int kNacc = kSB * kSB + kSB;          // Gram + row sums
 constexpr int LDS = kSB + 1;                    // padded leading dimension in shared memory
 constexpr int kMat = kSB * LDS;                 // floats per shared matrix
+
+// development: -DDWT_PROF_DENSE prints the clock of every phase of CTA 0 (build.py, DWT_NVCC_EXTRA)
+#ifdef DWT_PROF_DENSE
+#define PROF_DECL long long pt_[24]; int pn_ = 0
+#define PROF_MARK() do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.z == 0 && pn_ < 24) pt_[pn_++] = clock64(); } while (0)
+#define PROF_DUMP(name) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.z == 0) { printf(name ":"); for (int q_ = 1; q_ < pn_; ++q_) printf(" %lld", pt_[q_] - pt_[q_ - 1]); printf("\n"); } } while (0)
+#define PROF_ARGS , long long (&pt_)[24], int& pn_
+#define PROF_PASS , pt_, pn_
+#else
+#define PROF_DECL
+#define PROF_MARK()
+#define PROF_DUMP(name)
+#define PROF_ARGS
+#define PROF_PASS
+#endif
 
 // ------------------------------------------------------------------------------------------
 // partial_reduce: out[p][e] = sum_c partial[p][c][e]   (p = domain*SB + sb, fixed order over c)
@@ -90,100 +108,131 @@ __device__ __forceinline__ void store_block(float* M, const Blk& t, const float 
     for (int s = 0; s < 4; ++s) M[(4 * t.bi + r) * LDS + 4 * t.bj + s] = c[r][s];
 }
 
-// In-register right-looking Cholesky of the SPD matrix held as 4x4 blocks.  The blocks are held TRANSPOSED:
-// a[r][s] is element (i = 4*bj + s, j = 4*bi + r) -- for the symmetric input the same numbers as the (bi, bj) block, so
-// the caller fills `a` as if it were untransposed -- which puts the 16 owners of a COLUMN block (fixed bi) into one
-// half-warp: the pivot travels by shuffle and a step needs ONE block barrier (publish the scaled column, then every
-// thread applies the rank-1 update from the double-buffered sCol), not two (round 1: pivot through shared memory,
-// 128 barriers for a 64 x 64 group; profiles/ncu_r01i_tc_final.txt put 42 % of the kernel there).
-// On exit the entries with i >= j hold L[i][j].  False on a non-positive pivot.
-__device__ __forceinline__ bool cholesky_blocked(float (&a)[4][4], int GS, const Blk& t, float (*sCol)[kSB]) {
+// Blocked right-looking sweep: S = L L^T and W = L^-1 together, 4 columns per step, ONE block barrier per step.
+//
+//   a[r][s]  the SPD matrix, blocks held TRANSPOSED: element (i = 4*bj + s, j = 4*bi + r) -- for the symmetric input
+//            the same numbers as the (bi, bj) block, so the caller fills it as if it were untransposed.  The 16 owners
+//            of a COLUMN block (fixed bi) are one half-warp.
+//   b[r][s]  the running inverse, element (i = 4*bi + r, j = 4*bj + s); starts as I, ends as W.  The 16 owners of a ROW
+//            block are the same half-warp.
+//
+// Step k, in the half-warp bi == k: the diagonal thread factors its 4 x 4 block (4 square roots in one thread) and
+// hands L11 and 1/diag to the other 15 by shuffle; every thread solves its 4 x 4 block of the panel L21 = A21 L11^-T and
+// of the finished row block W_k = L11^-1 B_k and publishes both to shared memory (double-buffered).  After the barrier
+// every thread applies the rank-4 updates  A -= L21 L21^T  (blocks at or below the diagonal of the trailing matrix)
+// and  B -= L21 W_k  (rows below the panel, columns up to it).  16 steps of ~1000 cycles replace 64 single-column steps
+// (770 cycles each: sqrt, reciprocal, broadcast and barrier per column) plus a separate recursive-doubling inverse
+// through shared memory -- 78 k cycles of the 84 k of this kernel at gs = 64 (phase clocks, profiles/dense_r02.md).
+// Returns false on a non-positive pivot.
+struct PanelSmem {
+  float L[2][kSB][4];      // L[i][4k + p] of the current panel, 0 for rows i < 4k + 4
+  float W[2][4][kSB];      // W[4k + p][j], the finished row block
+};
+
+__device__ __forceinline__ bool factor_and_invert(float (&a)[4][4], float (&b)[4][4], int GS, const Blk& t, PanelSmem& sp) {
   bool ok = true;
   const unsigned hmask = (threadIdx.x & 16) ? 0xFFFF0000u : 0x0000FFFFu;
-  for (int k = 0; k < GS; ++k) {
-    const int kb = k >> 2, kk = k & 3, buf = k & 1;
-    if (t.bi == kb) {                               // the half-warp that owns column k (j == k  <=>  r == kk)
-      float pv = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q == kk) pv = a[q][q];                  // meaningful in the diagonal thread bj == kb
-      pv = __shfl_sync(hmask, pv, kb, 16);
-      ok = ok && (pv > 0.f);
-      const float d = sqrtf(pv), inv = 1.f / d;
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int s = 0; s < 4; ++s) b[r][s] = (t.act && t.bi == t.bj && r == s) ? 1.f : 0.f;
+  const int nsteps = GS >> 2;
+  for (int k = 0; k < nsteps; ++k) {
+    const int buf = k & 1;
+    if (t.bi == k) {                                  // half-warp uniform
+      // --- diagonal block: unblocked 4 x 4 Cholesky in the thread bj == k.  The other 15 run the same instructions on
+      //     the identity (no divergence before the shuffles, and no special-case slow path of the square root on the
+      //     arbitrary numbers of an off-diagonal block -- that cost 2000 cycles per step).  Only 1/diag(L11) is ever
+      //     used (L itself is not an output): reciprocal square root + one Newton step, no square root, no division.
+      float l[4][4], inv[4];                          // l[i][j], i >= j
+      const bool diag = t.bj == k;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) l[i][j] = diag ? a[j][i] : (i == j ? 1.f : 0.f);
+      bool pos = true;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float x = l[p][p];
+        pos = pos && (x > 0.f);
+        const float y = rsqrtf(x);
+        inv[p] = y * fmaf(-0.5f * x * y, y, 1.5f);   // y (3 - x y^2) / 2
+#pragma unroll
+        for (int i = p + 1; i < 4; ++i) l[i][p] *= inv[p];
+#pragma unroll
+        for (int j = p + 1; j < 4; ++j)
+#pragma unroll
+          for (int i = j; i < 4; ++i) l[i][j] = fmaf(-l[i][p], l[j][p], l[i][j]);
+      }
+      const int src = k;                              // lane of the diagonal thread inside the half-warp
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        inv[i] = __shfl_sync(hmask, inv[i], src, 16);
+#pragma unroll
+        for (int j = 0; j < i; ++j) l[i][j] = __shfl_sync(hmask, l[i][j], src, 16);
+      }
+      pos = __shfl_sync(hmask, pos ? 1 : 0, src, 16) != 0;
+      ok = ok && pos;
+      // --- panel of L: rows 4*bj + s, x L11^T = a  (forward substitution along the 4 columns)
+      const bool below = t.bj > k;
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        const int i = 4 * t.bj + s;
+        float x0 = a[0][s] * inv[0];
+        float x1 = fmaf(-x0, l[1][0], a[1][s]) * inv[1];
+        float x2 = fmaf(-x1, l[2][1], fmaf(-x0, l[2][0], a[2][s])) * inv[2];
+        float x3 = fmaf(-x2, l[3][2], fmaf(-x1, l[3][1], fmaf(-x0, l[3][0], a[3][s]))) * inv[3];
+        if (!below) { x0 = x1 = x2 = x3 = 0.f; }
+        *reinterpret_cast<float4*>(&sp.L[buf][4 * t.bj + s][0]) = make_float4(x0, x1, x2, x3);
+      }
+      // --- finished row block of W: L11 x = b  (columns 4*bj + s; zero right of the diagonal block by construction)
+      float w[4][4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-          if (r == kk) {
-            float v = a[r][s];
-            v = (i > k) ? v * inv : ((i == k) ? d : v);
-            a[r][s] = v;
-            sCol[buf][i] = (i > k) ? v : 0.f;
-          }
+      for (int s = 0; s < 4; ++s) {
+        w[0][s] = b[0][s] * inv[0];
+        w[1][s] = fmaf(-l[1][0], w[0][s], b[1][s]) * inv[1];
+        w[2][s] = fmaf(-l[2][1], w[1][s], fmaf(-l[2][0], w[0][s], b[2][s])) * inv[2];
+        w[3][s] = fmaf(-l[3][2], w[2][s], fmaf(-l[3][1], w[1][s], fmaf(-l[3][0], w[0][s], b[3][s]))) * inv[3];
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) b[r][s] = w[r][s];
+        *reinterpret_cast<float4*>(&sp.W[buf][r][4 * t.bj]) = make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
       }
     }
     __syncthreads();
-    if (t.act) {                                    // rank-1 update of the trailing matrix (sCol is 0 for rows <= k)
-      float ci[4], cj[4];
+    if (t.act && t.bi > k) {
+      float li[4][4];                                 // panel rows 4*bi + r
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { ci[q] = sCol[buf][4 * t.bj + q]; cj[q] = sCol[buf][4 * t.bi + q]; }
+      for (int r = 0; r < 4; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(&sp.L[buf][4 * t.bi + r][0]);
+        li[r][0] = v.x; li[r][1] = v.y; li[r][2] = v.z; li[r][3] = v.w;
+      }
+      if (t.bj >= t.bi) {                             // a(i = 4bj+s, j = 4bi+r) -= sum_p L[i][p] L[j][p]
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+        for (int s = 0; s < 4; ++s) {
+          const float4 v = *reinterpret_cast<const float4*>(&sp.L[buf][4 * t.bj + s][0]);
 #pragma unroll
-        for (int s = 0; s < 4; ++s) a[r][s] = fmaf(-cj[r], ci[s], a[r][s]);
+          for (int r = 0; r < 4; ++r)
+            a[r][s] = fmaf(-v.w, li[r][3], fmaf(-v.z, li[r][2], fmaf(-v.y, li[r][1], fmaf(-v.x, li[r][0], a[r][s]))));
+        }
+      }
+      if (t.bj <= k) {                                // b(i = 4bi+r, j = 4bj+s) -= sum_p L[i][p] W[p][j]
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float4 v = *reinterpret_cast<const float4*>(&sp.W[buf][p][4 * t.bj]);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            b[r][0] = fmaf(-li[r][p], v.x, b[r][0]);
+            b[r][1] = fmaf(-li[r][p], v.y, b[r][1]);
+            b[r][2] = fmaf(-li[r][p], v.z, b[r][2]);
+            b[r][3] = fmaf(-li[r][p], v.w, b[r][3]);
+          }
+        }
+      }
     }
   }
   return ok;
-}
-
-// W = L^-1 for lower-triangular L (GS x GS in shared memory, zeros above the diagonal).  Diagonal
-// 4x4 blocks are inverted by one thread each, then block sizes double: W21 = -W22 (L21 W11).
-__device__ __forceinline__ void tri_inverse(const float* sL, float* sW, float* sT, int GS) {
-  for (int e = threadIdx.x; e < GS * LDS; e += blockDim.x) sW[e] = 0.f;
-  __syncthreads();
-  if ((int)threadIdx.x < GS / 4) {
-    const int o = 4 * threadIdx.x;
-    float l[4][4], w[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int s = 0; s < 4; ++s) { l[r][s] = sL[(o + r) * LDS + o + s]; w[r][s] = 0.f; }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      w[j][j] = 1.f / l[j][j];
-#pragma unroll
-      for (int i = j + 1; i < 4; ++i) {
-        float acc = 0.f;
-#pragma unroll
-        for (int k = j; k < i; ++k) acc = fmaf(l[i][k], w[k][j], acc);
-        w[i][j] = -acc / l[i][i];
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int s = 0; s < 4; ++s) sW[(o + r) * LDS + o + s] = w[r][s];
-  }
-  __syncthreads();
-  for (int s = 4; s < GS; s <<= 1) {
-    // pair p: off-diagonal block rows [2ps+s, 2ps+2s) x cols [2ps, 2ps+s)
-    const int npairs = GS / (2 * s), nel = npairs * s * s;
-    for (int e = threadIdx.x; e < nel; e += blockDim.x) {      // T = L21 * W11  (W11 lower-triangular)
-      const int p = e / (s * s), r = (e / s) % s, c = e % s, r0 = 2 * p * s + s, c0 = 2 * p * s;
-      float acc = 0.f;
-      for (int k = c; k < s; ++k) acc = fmaf(sL[(r0 + r) * LDS + c0 + k], sW[(c0 + k) * LDS + c0 + c], acc);
-      sT[(r0 + r) * LDS + c0 + c] = acc;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < nel; e += blockDim.x) {      // W21 = -W22 * T  (W22 lower-triangular)
-      const int p = e / (s * s), r = (e / s) % s, c = e % s, r0 = 2 * p * s + s, c0 = 2 * p * s;
-      float acc = 0.f;
-      for (int k = 0; k <= r; ++k) acc = fmaf(sW[(r0 + r) * LDS + r0 + k], sT[(r0 + k) * LDS + c0 + c], acc);
-      sW[(r0 + r) * LDS + c0 + c] = -acc;
-    }
-    __syncthreads();
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -193,28 +242,25 @@ __device__ __forceinline__ void tri_inverse(const float* sL, float* sW, float* s
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fwd_factor_kernel(const float* __restrict__ gram, const float* __restrict__ shift,
                                                          const Geom gm, const FwdFin f) {
-  extern __shared__ __align__(16) float dsm[];
-  float* sL = dsm;                 // Cholesky factor
-  float* sW = sL + kMat;           // its inverse
-  float* sT = sW + kMat;           // scratch of the inverse
-  float* sC = sT + kMat;           // un-shrunk covariance (for the EMA)
-  __shared__ float sCol[2][kSB], sMean[kSB];
+  __shared__ __align__(16) PanelSmem sp;
+  __shared__ float sC[kMat];       // un-shrunk covariance (for the EMA)
+  __shared__ float sMean[kSB], sRow[kSB];
   __shared__ int sBad, sBadDom;
   const int g = blockIdx.x, GS = gm.GS, nb = kSB / GS, sb = g / nb, o = (g % nb) * GS;
   const Blk t(GS);
   const int SB = (gm.C + kSB - 1) / kSB;
   const float invM = 1.f / gm.M;
   if (threadIdx.x == 0) sBad = 0;
+  PROF_DECL;
+  PROF_MARK();
   for (int d = 0; d < gm.D; ++d) {
     const float* G = gram ? gram + ((size_t)d * SB + sb) * kNacc : nullptr;
     const size_t gbase = ((size_t)d * gm.G + g) * GS * GS;
-    for (int i = threadIdx.x; i < GS; i += blockDim.x) {
-      const float mu = G ? shift[((size_t)d * SB + sb) * kSB + o + i] + G[kSB * kSB + o + i] * invM
-                         : f.rmean[d][g * GS + i];
-      sMean[i] = mu;
-      f.save_mean[(size_t)d * gm.C + g * GS + i] = mu;
-    }
-    float a[4][4];
+    // every global load of this domain is issued before the first dependent instruction: the Gram block, the row
+    // sums, and the running buffers the EMA needs at the very end (their latency hides behind the factorisation;
+    // the previous domain's stores precede this point by a block barrier, so aliased buffers still see the ordered
+    // sequence)
+    float graw[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -222,19 +268,15 @@ __global__ void __launch_bounds__(256) fwd_factor_kernel(const float* __restrict
         float v = 0.f;
         if (t.act) {
           const int i = 4 * t.bi + r, j = 4 * t.bj + s, hi = i > j ? i : j, lo = i > j ? j : i;
-          float cov;
-          if (G) {
-            cov = G[(o + hi) * kSB + o + lo] * invM - (G[kSB * kSB + o + i] * invM) * (G[kSB * kSB + o + j] * invM);
-            sC[i * LDS + j] = cov;
-          } else {
-            cov = f.rcov[d][(size_t)g * GS * GS + i * GS + j];
-          }
-          v = f.a * cov + (i == j ? f.b : 0.f);
+          v = G ? __ldcg(G + (o + hi) * kSB + o + lo) : f.rcov[d][(size_t)g * GS * GS + i * GS + j];
         }
-        a[r][s] = v;
+        graw[r][s] = v;
       }
-    // the running buffers of this domain are fetched NOW (their latency hides behind the factorisation); the previous
-    // domain's stores precede this point by a block barrier, so aliased buffers still see the ordered sequence
+    float rowsum = 0.f, shf = 0.f;
+    if ((int)threadIdx.x < GS) {
+      if (G) { rowsum = __ldcg(G + kSB * kSB + o + threadIdx.x); shf = shift[((size_t)d * SB + sb) * kSB + o + threadIdx.x]; }
+      else shf = f.rmean[d][g * GS + threadIdx.x];
+    }
     constexpr int kEmaPer = kSB * kSB / 256;
     float rc_old[kEmaPer], rm_old = 0.f;
     const bool ema = G != nullptr && f.update_running;
@@ -246,20 +288,42 @@ __global__ void __launch_bounds__(256) fwd_factor_kernel(const float* __restrict
       }
       if ((int)threadIdx.x < GS) rm_old = f.rmean[d][g * GS + threadIdx.x];
     }
+    if ((int)threadIdx.x < GS) {
+      const float mu = G ? shf + rowsum * invM : shf;
+      sMean[threadIdx.x] = mu;
+      sRow[threadIdx.x] = rowsum * invM;              // mean of the shifted samples
+      f.save_mean[(size_t)d * gm.C + g * GS + threadIdx.x] = mu;
+    }
     if (threadIdx.x == 0) sBadDom = 0;
     __syncthreads();
-    if (!cholesky_blocked(a, GS, t, sCol)) { sBad = 1; sBadDom = 1; }
-    if (t.act) {                                    // a[r][s] = element (i = 4bj+s, j = 4bi+r): keep the lower triangle
+    float a[4][4], w[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        float v = 0.f;
+        if (t.act) {
+          const int i = 4 * t.bi + r, j = 4 * t.bj + s;
+          float cov = graw[r][s];
+          if (G) {
+            cov = cov * invM - sRow[i] * sRow[j];
+            sC[i * LDS + j] = cov;
+          }
+          v = f.a * cov + (i == j ? f.b : 0.f);
+        }
+        a[r][s] = v;
+      }
+    PROF_MARK();
+    if (!factor_and_invert(a, w, GS, t, sp)) { sBad = 1; sBadDom = 1; }
+    PROF_MARK();
+    if (t.act) {                                      // w[r][s] = W(4bi + r, 4bj + s): straight from the registers
 #pragma unroll
       for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-          sL[(4 * t.bj + s) * LDS + 4 * t.bi + r] = (4 * t.bi + r <= 4 * t.bj + s) ? a[r][s] : 0.f;
+        *reinterpret_cast<float4*>(f.save_w + gbase + (size_t)(4 * t.bi + r) * GS + 4 * t.bj) =
+            make_float4(w[r][0], w[r][1], w[r][2], w[r][3]);
     }
-    __syncthreads();
-    tri_inverse(sL, sW, sT, GS);
-    for (int e = threadIdx.x; e < GS * GS; e += blockDim.x) f.save_w[gbase + e] = sW[(e / GS) * LDS + e % GS];
-    if (ema && !sBadDom) {                         // a non-PD batch covariance never reaches the running buffers
+    __syncthreads();                                  // sC complete, sBadDom final
+    if (ema && !sBadDom) {                            // a non-PD batch covariance never reaches the running buffers
       const float m = f.momentum, k = 1.f - f.momentum;
 #pragma unroll
       for (int n = 0; n < kEmaPer; ++n) {
@@ -269,7 +333,9 @@ __global__ void __launch_bounds__(256) fwd_factor_kernel(const float* __restrict
       if ((int)threadIdx.x < GS) f.rmean[d][g * GS + threadIdx.x] = m * sMean[threadIdx.x] + k * rm_old;
     }
     __syncthreads();      // also orders this domain's buffer writes before the next domain's reads (aliasing)
+    PROF_MARK();
   }
+  PROF_DUMP("fwd_factor load|factor+invert|save+ema");
   if (threadIdx.x == 0 && sBad) atomicOr(f.status, DWT_STATUS_NOT_PD);
 }
 
@@ -292,17 +358,38 @@ __global__ void __launch_bounds__(256) bwd_coef_kernel(const float* __restrict__
   const float* G = rgram ? rgram + ((size_t)d * SB + sb) * kNacc : nullptr;
   const size_t gbase = ((size_t)d * gm.G + g) * GS * GS;
   float* coef = f.coef + ((size_t)d * gm.G + g) * coef_stride(GS);
-  for (int e = threadIdx.x; e < GS * GS; e += blockDim.x) {
-    const int i = e / GS, j = e - i * GS;
-    sW[i * LDS + j] = f.save_w[gbase + e];
-    sR[i * LDS + j] = (G && train) ? G[(o + i) * kSB + o + j] : 0.f;
+  PROF_DECL;
+  PROF_MARK();
+  // all global loads first (interleaved with their shared-memory stores the compiler kept them in order: 16 dependent
+  // round trips, 17.7 k of this kernel's 44 k cycles at gs = 64); GS is a power of two: shifts, not divisions
+  const int gsh = __ffs(GS) - 1;
+  const float invM = 1.f / gm.M;
+  constexpr int kPer = kSB * kSB / 256;
+  float wv[kPer], rv[kPer];
+#pragma unroll
+  for (int n = 0; n < kPer; ++n) {
+    const int e = threadIdx.x + 256 * n, i = e >> gsh, j = e & (GS - 1);
+    const bool in = e < GS * GS;
+    wv[n] = in ? f.save_w[gbase + e] : 0.f;
+    rv[n] = (in && G && train) ? __ldcg(G + (o + i) * kSB + o + j) : 0.f;
   }
-  for (int i = threadIdx.x; i < GS; i += blockDim.x) {
-    sSdz[i] = (G && train) ? G[kSB * kSB + o + i] : 0.f;
-    sMu[i] = f.save_mean[(size_t)d * gm.C + g * GS + i];
-    if (dybar) dybar[((size_t)d * SB + sb) * kSB + o + i] = sSdz[i] / gm.M;      // mean_M dy (0 in eval mode)
+  float sdz = 0.f, mu = 0.f;
+  if ((int)threadIdx.x < GS) {
+    sdz = (G && train) ? __ldcg(G + kSB * kSB + o + threadIdx.x) : 0.f;
+    mu = f.save_mean[(size_t)d * gm.C + g * GS + threadIdx.x];
+  }
+#pragma unroll
+  for (int n = 0; n < kPer; ++n) {
+    const int e = threadIdx.x + 256 * n, i = e >> gsh, j = e & (GS - 1);
+    if (e < GS * GS) { sW[i * LDS + j] = wv[n]; sR[i * LDS + j] = rv[n]; }
+  }
+  if ((int)threadIdx.x < GS) {
+    sSdz[threadIdx.x] = sdz * invM;                   // mean_M dy (0 in eval mode)
+    sMu[threadIdx.x] = mu;
+    if (dybar) dybar[((size_t)d * SB + sb) * kSB + o + threadIdx.x] = sdz * invM;
   }
   __syncthreads();
+  PROF_MARK();
   float c[4][4];
   if (train) {
     mm_block<false, true>(sR, sW, GS, t, c);               // R W^T ; P = Phi(-R W^T)
@@ -315,34 +402,44 @@ __global__ void __launch_bounds__(256) bwd_coef_kernel(const float* __restrict__
       }
     store_block(sT1, t, c);
     __syncthreads();
+    PROF_MARK();
     mm_block<true, false>(sW, sT1, GS, t, c);              // T = W^T P
     store_block(sT2, t, c);
     __syncthreads();
+    PROF_MARK();
     mm_block<false, false>(sT2, sW, GS, t, c);             // S' = T W
     store_block(sT1, t, c);
     __syncthreads();
+    PROF_MARK();
   }
-  const float sc = f.a / gm.M;
-  for (int e = threadIdx.x; e < GS * GS; e += blockDim.x) {
-    const int i = e / GS, j = e - i * GS;
-    const float bm = train ? sc * (sT1[i * LDS + j] + sT1[j * LDS + i]) : 0.f;
-    coef[e] = (j >= i) ? sW[j * LDS + i] : 0.f;            // A1 = W^T
-    coef[GS * GS + e] = bm;
-    sT2[i * LDS + j] = bm;
+  const float sc = f.a * invM;
+#pragma unroll
+  for (int n = 0; n < kPer; ++n) {
+    const int e = threadIdx.x + 256 * n, i = e >> gsh, j = e & (GS - 1);
+    if (e < GS * GS) {
+      const float bm = train ? sc * (sT1[i * LDS + j] + sT1[j * LDS + i]) : 0.f;
+      coef[e] = (j >= i) ? sW[j * LDS + i] : 0.f;          // A1 = W^T
+      coef[GS * GS + e] = bm;
+      sT2[i * LDS + j] = bm;
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < GS; i += blockDim.x) {
+  // cvec_i = -(sum_j W_ji mean(dy)_j + sum_j Bm_ij mu_j): 4 threads per row, partial sums met by shuffle
+  {
+    const int i = threadIdx.x >> 2, q = threadIdx.x & 3;
     float cv = 0.f;
-    if (train) {
-      for (int j = i; j < GS; ++j) cv = fmaf(sW[j * LDS + i], sSdz[j] / gm.M, cv);
-      for (int j = 0; j < GS; ++j) cv = fmaf(sT2[i * LDS + j], sMu[j], cv);
-      cv = -cv;
+    if (train && i < GS) {
+      for (int j = q; j < GS; j += 4) cv = fmaf(sW[j * LDS + i], sSdz[j], fmaf(sT2[i * LDS + j], sMu[j], cv));   // W_ji = 0 for j < i
     }
-    coef[2 * GS * GS + i] = cv;
+    cv += __shfl_xor_sync(0xffffffffu, cv, 1);
+    cv += __shfl_xor_sync(0xffffffffu, cv, 2);
+    if (q == 0 && i < GS) coef[2 * GS * GS + i] = -cv;
   }
+  PROF_MARK();
+  PROF_DUMP("bwd_coef load|mm1|mm2|mm3|tail");
 }
 
-constexpr size_t kFactorSmem = sizeof(float) * 4 * kMat;
+constexpr size_t kFactorSmem = 0;   // fwd_factor: static shared memory only (panel buffers + covariance)
 constexpr size_t kCoefSmem = sizeof(float) * 4 * kMat;
 
 }  // namespace

@@ -273,47 +273,55 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// One lane's share of a landed tile: the 32 pixels of its channel row (8 swizzled 16-byte chunks; the 32 lanes of a
-// warp own 32 consecutive rows: four conflict-free wavefronts per access).  s = x - shift inside the tensor, 0 outside;
-// hi = RN_tf32(s) (an exact tf32 value: nothing depends on how the core would round), lo = s - hi (exact in fp32,
-// |lo| <= 2^-12 |s|; the core keeps its top 11 bits: a relative 2^-22 of s, sign-symmetric).
-//   LO = false (hi warps): hand hi to tensor memory AND write it back in place (the B operand);
-//   LO = true  (lo warps): hand lo to tensor memory.
-// Warps are homogeneous (no divergent halves): the tile is read from shared memory twice (the hi warp and the lo warp
-// of the same 32 rows meet at a named barrier between the reads and the write-back), but every ALU instruction
-// does useful work in all 32 lanes -- the interleaved hi/lo-in-one-warp variant read it once and was issue-bound
-// (1230 warp instructions per tile, 0.58 of the HBM peak; profiles/ncu_r02_tc_gram.md).
-template <bool LO>
-__device__ __forceinline__ void gram_transform_row(uint32_t tile, int row, float shift, int px0, int HW, bool rowok,
-                                                   uint32_t tmem_a, int pair_barrier) {
-  const uint32_t rbase = tile + 128u * (uint32_t)row;
-  const int sw = row & 7;
-  float v[32];
+// Transform of one landed tile by one warp.  s = x - shift inside the tensor, 0 outside (the 32 lanes of a warp read 16
+// distinct 128-byte rows, 8 swizzled 16-byte chunks each).  A warp may only touch its own 32 TMEM lanes, and WHICH
+// A-operand row lives in which lane is free (D row r is just A row r times B): quarter q carries channels 16q..16q+15,
+// lanes 0..15 their hi rows and lanes 16..31 their lo rows.  The tensor core reads the top 19 bits of an fp32 word, so
+// hi = trunc_tf32(s) needs NO instruction: the hi lanes hand s itself to tensor memory and write s back in place as the
+// B operand (both truncated alike by the core: HH stays symmetric), the lo lanes hand over lo = s - trunc_tf32(s)
+// (exact in fp32, |lo| < 2^-10 |s|; the core keeps its top 11 bits).  One instruction stream serves both halves:
+// out = s - (s & mask), mask = 0 in the hi lanes (s - 0 = s) and 0xFFFFE000 in the lo lanes.  Per warp and tile:
+// 8 LDS.128 + 32 FADD (shift) + 8 predicated STS.128 + 32 LOP3 + 32 FADD + 1 tcgen05.st.  An earlier form with
+// homogeneous hi warps / lo warps and round-to-nearest (two integer instructions per element in both, the tile read
+// twice, the pairs meeting at a named barrier) needed 1040 warp instructions per tile against 720 here
+// (profiles/ncu_r02_tc_gram.md).  Truncation instead of rounding leaves lo one bit longer: the dropped lo lo^T term is
+// 3e-7 of the covariance (RN: 3e-8), a near-uniform scale of the diagonal that the whitened output does not see
+// (tools/tf32_gram_accuracy.py: y error unchanged).
+// (Waiting for the tensor-memory slot only before the final tcgen05.st, after the arithmetic, was slower -- 186 us against
+// 172: the two sets then compute concurrently and delay the OLDER tile, which is the one the MMA issuers wait for.)
+__device__ __forceinline__ void gram_transform_quarter(uint32_t tile, int ch, bool hi_lane, uint32_t lomask, float shift, int px0,
+                                                       int HW, bool rowok, uint32_t tmem_a) {
+  const uint32_t rbase = tile + 128u * (uint32_t)ch;
+  const int sw = ch & 7;
+  float2 v[16];                      // pairs: Blackwell's packed fp32 add halves the instruction count of both passes
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 t4 = lds128(rbase + 16u * (uint32_t)(j ^ sw));
-    v[4 * j] = t4.x; v[4 * j + 1] = t4.y; v[4 * j + 2] = t4.z; v[4 * j + 3] = t4.w;
+    v[2 * j] = make_float2(t4.x, t4.y); v[2 * j + 1] = make_float2(t4.z, t4.w);
   }
   if (rowok && px0 + kTilePx <= HW) {
+    const float2 ns = make_float2(-shift, -shift);               // x + (-K) == x - K
 #pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] -= shift;
+    for (int k = 0; k < 16; ++k) v[k] = __fadd2_rn(v[k], ns);
   } else {
 #pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = (rowok && px0 + k < HW) ? v[k] - shift : 0.f;
+    for (int k = 0; k < 16; ++k) {
+      v[k].x = (rowok && px0 + 2 * k < HW) ? v[k].x - shift : 0.f;
+      v[k].y = (rowok && px0 + 2 * k + 1 < HW) ? v[k].y - shift : 0.f;
+    }
   }
-  // the hi warp overwrites the rows its partner lo warp reads: both have consumed their loads (the subtraction above)
-  // before either passes this 64-thread named barrier
-  asm volatile("bar.sync %0, 64;" ::"r"(pair_barrier) : "memory");
-  if constexpr (LO) {
+  if (hi_lane) {                     // lanes l and l + 16 loaded the same row in the same instruction: no hazard
 #pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] -= round_tf32(v[k]);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = round_tf32(v[k]);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sts128(rbase + 16u * (uint32_t)(j ^ sw), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < 8; ++j) sts128(rbase + 16u * (uint32_t)(j ^ sw), v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
   }
-  tmem_st32(tmem_a, v);
+  // out = s + (-(s & mask)): one LOP3 per element ((s & mask) ^ sign; -0 in the hi lanes, and s + -0 == s), one packed add per pair
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float2 t = make_float2(__uint_as_float((__float_as_uint(v[k].x) & lomask) ^ 0x80000000u),
+                                 __uint_as_float((__float_as_uint(v[k].y) & lomask) ^ 0x80000000u));
+    v[k] = __fadd2_rn(v[k], t);
+  }
+  tmem_st32(tmem_a, reinterpret_cast<const float(&)[32]>(v));
 }
 
 // Shared-memory stage of the Gram kernel: the landed [64 ch x 32 px] tile followed by 16 constant rows -- row 64 all
@@ -393,10 +401,10 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
   const uint32_t tmem_d = tmem, tmem_a0 = tmem + NACCUM * kGramN;   // accumulators: columns 0..159; A slots from column 160
 
   // transform-warp geometry: two sets of four warps take alternate tiles; a warp may only touch the TMEM quarter
-  // warp & 3: quarters 0, 1 = hi rows of channels 0..63 (lane = channel), quarters 2, 3 = their lo rows
+  // warp & 3, which carries channels 16q..16q+15: hi rows in lanes 0..15, lo rows in lanes 16..31
   const int quad = warp & 3, set = (warp - 2) >> 2;
-  const bool lo_warp = quad >= 2;
-  const int row = 32 * (quad & 1) + lane;
+  const bool lo_lane = lane >= 16;                 // see gram_transform_quarter
+  const int row = 16 * quad + (lane & 15);         // channel row of the tile this lane handles
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -437,7 +445,6 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
     const float shift = sShift[row];
     const bool rowok = (ch0 + row) < gm.C;
     const uint32_t smem0 = smem_u32(smem), ta0 = tmem_a0 + ((uint32_t)(quad * 32) << 16);
-    const int pair_bar = 1 + 2 * set + (quad & 1);       // hi warp (quarter q) and lo warp (quarter q + 2) of the same rows
     const int t0 = tr.begin + set;
     int n = t0 / tr.PB, pb = t0 - n * tr.PB;
     for (int it = set; it < ntiles; it += 2) {
@@ -446,8 +453,7 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
       if (u >= 0) mbar_wait(&bars.a_empty[u % (2 * NA)], (u / (2 * NA)) & 1);
       tc_fence_after();
       const uint32_t tile = smem0 + (uint32_t)(s * kGramStageBytes), ta = ta0 + (uint32_t)(a * kTilePx);
-      if (lo_warp) gram_transform_row<true>(tile, row, shift, pb * kTilePx, gm.HW, rowok, ta, pair_bar);
-      else gram_transform_row<false>(tile, row, shift, pb * kTilePx, gm.HW, rowok, ta, pair_bar);
+      gram_transform_quarter(tile, row, !lo_lane, lo_lane ? 0xFFFFE000u : 0u, shift, pb * kTilePx, gm.HW, rowok, ta);
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
@@ -487,14 +493,14 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
     }
     tc_fence_before();
     rs = tail[0];                                  // sum over the CTA's samples of hi (hi rows) / lo (lo rows)
-    if (lo_warp) {
+    if (lo_lane) {
 #pragma unroll
       for (int j = 0; j < kTileCh; ++j) sT[row * (kTileCh + 1) + j] = P[j];          // LH[row][j]
       sRS[row] = rs;
     }
   }
   __syncthreads();
-  if (epi_warp && !lo_warp) {
+  if (epi_warp && !lo_lane) {
     if (ntiles > 0) {
 #pragma unroll
       for (int j4 = 0; j4 < kTileCh / 4; ++j4) {

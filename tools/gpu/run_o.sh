@@ -1,0 +1,16 @@
+#!/bin/bash
+# round-2 GPU call O (1 GPU): tc_gram quarter-per-warp transform (trunc split) vs the homogeneous hi/lo warps
+mkdir -p gpurun_out/o
+timeout 600 python -m pytest tests/test_gpu_parity_r2.py tests/test_gpu_parity.py -m gpu -q -s -p no:cacheprovider -k "tensor_core or run_to_run or non_pd or whitening_vs or microbench_shape or fused_triple or graph_capturable" > gpurun_out/o/pytest_tc.log 2>&1; echo "pytest tc rc=$?"
+grep -E "passed|failed|error" gpurun_out/o/pytest_tc.log | tail -3
+for q in 1 0 1; do
+DWT_GRAM_Q=$q timeout 600 python bench.py --workload microbench --no-cpu-baseline > gpurun_out/o/micro_q$q.json 2> gpurun_out/o/micro_q$q.err; echo "micro q=$q rc=$?"
+python - <<PY
+import json
+try:
+    mb=json.loads(open("gpurun_out/o/micro_q$q.json").read().strip().splitlines()[-1])
+    print("micro q=$q", mb["ms_per_step"], mb["roofline"]["frac"], {k: round(v["us_per_launch"],1) for k,v in sorted(mb.get("kernels",{}).items())})
+except Exception as e: print("micro parse failed", e)
+PY
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'tc_gram' -s 1 -c 1 -o gpurun_out/o/prof_gram python tools/micro_once.py 256 > gpurun_out/o/ncu_gram.log 2>&1; echo "ncu rc=$?"
