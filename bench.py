@@ -129,12 +129,15 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- model
-def build_model(layers, device, site_mode, seed=1, channels_last=False, stem_pad=0, stem_nchw=False):
+DEFAULT_STEM = "s2d"     # harness option, same arithmetic (harness/resnet50_dwt.py _stem_s2d); --stem direct for the plain call
+
+
+def build_model(layers, device, site_mode, seed=1, channels_last=False, stem_pad=0, stem_nchw=False, stem_s2d=False):
     from harness.resnet50_dwt import build_resnet50_dwt
     from harness.synth import synth_state_dict
     sd = {k: v.to(device) for k, v in synth_state_dict(seed=seed).items()}
     model = build_resnet50_dwt(sd, layers, site_mode=site_mode, channels_last=channels_last, stem_pad=stem_pad,
-                               stem_nchw=stem_nchw).to(device)
+                               stem_nchw=stem_nchw, stem_s2d=stem_s2d).to(device)
     return model.train()
 
 
@@ -375,6 +378,8 @@ def workload_config(args, per_domain):
 def implementation_note(args):
     seg = getattr(args, "grad_segments", 1)
     return {"site_mode": args.site_mode, "memory_format": args.memory_format,
+            "stem": ("7x7/2 stem convolution evaluated as the 4x4/1 convolution of the 2x2 space-to-depth image (same arithmetic, "
+                     "cuDNN tensor-core kernel)" if getattr(args, "stem", DEFAULT_STEM) == "s2d" else "7x7/2 convolution on the 3-channel image"),
             "launch": "CUDA-graph replay of the whole step" if args.cuda_graph else "eager",
             "grad_gather": getattr(args, "grad_gather", "accumulate"),
             "grad_sync": ("flat fp32 gradient buffer, one NCCL all-reduce (AVG) per step after backward" if seg == 1 else
@@ -519,7 +524,8 @@ def run_ours(args):
         return
 
     nhwc = args.memory_format == "nhwc"
-    model = build_model(dwt_b200, device, args.site_mode, channels_last=nhwc, stem_pad=args.stem_pad, stem_nchw=args.stem_nchw)
+    model = build_model(dwt_b200, device, args.site_mode, channels_last=nhwc, stem_pad=args.stem_pad, stem_nchw=args.stem_nchw,
+                        stem_s2d=args.stem == "s2d")
     net = model
     sync = FlatGradAllReduce(model, world, segments=args.grad_segments, gather=args.grad_gather) if distributed else None   # one GPU: plain .grad tensors
     opt = make_optimizer(model)
@@ -844,6 +850,8 @@ def main():
     ap.add_argument("--sites-out", default="", help="write the per-site kernel table (JSON) here")
     ap.add_argument("--stem-pad", type=int, default=0, choices=[0, 4, 8],
                     help="zero-pad the 3-channel image (and the stem weight) to this many channels for cuDNN")
+    ap.add_argument("--stem", default=DEFAULT_STEM, choices=["direct", "s2d"],
+                    help="s2d: the 7x7/2 stem convolution as a 4x4/1 convolution of the 2x2 space-to-depth image (same arithmetic)")
     ap.add_argument("--stem-nchw", action="store_true", help="run only the 3-channel stem convolution in NCHW (experiment)")
     ap.add_argument("--grad-gather", choices=["accumulate", "copy"], default="copy",
                     help="how gradients reach the flat all-reduce buffer: autograd accumulates into views of it, or one "

@@ -143,8 +143,14 @@ class Bottleneck(_SiteOwner):
 
 
 class ResNet50DWT(_SiteOwner):
-    def __init__(self, layers, state_dict, num_classes=65, group_size=4, site_mode="modules", stem_pad=0, stem_nchw=False):
+    def __init__(self, layers, state_dict, num_classes=65, group_size=4, site_mode="modules", stem_pad=0, stem_nchw=False,
+                 stem_s2d=False):
         super().__init__()
+        # stem_s2d: evaluate the 7x7 / stride-2 / pad-3 stem convolution as the 4x4 / stride-1 convolution of the 2x2
+        # space-to-depth rearrangement of the image (12 channels) -- see _stem_s2d.  Same sums of the same products; the
+        # 12-channel operand gives cuDNN a tensor-core implicit-GEMM kernel where the 3-channel one only has legacy
+        # engines (2.0 ms forward + 2.2 ms weight gradient per step on B200, profiles/launches_r02_step.md).
+        self.stem_s2d = stem_s2d
         # stem_nchw: run ONLY the 3-channel 7x7 stem convolution in NCHW (its weight stays NCHW-contiguous, the image is
         # viewed / copied to NCHW, the 64-channel result is copied to channels-last once) -- cuDNN's NHWC engines for a
         # 3-channel input are legacy kernels (profiles/launches_r02_step.md); same arithmetic, different cuDNN kernel
@@ -179,7 +185,32 @@ class ResNet50DWT(_SiteOwner):
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
+    def _stem_s2d(self, x):
+        """conv(x, w; k=7, s=2, p=3)[o, i, j] = sum_{c,u,v} w[o,c,u,v] xp[c, 2i+u, 2j+v]   (xp: x padded by 3).
+        Write u = 2u' + a, v = 2v' + b (a, b in {0,1}; u', v' in 0..3; the taps u = 7 / v = 7 get a zero weight):
+            = sum_{(c,a,b),u',v'} w4[o,(c,a,b),u',v'] xs[(c,a,b), i+u', j+v']
+        with xs[(c,a,b), p, q] = xp[c, 2p+a, 2q+b] and w4[o,(c,a,b),u',v'] = w[o,c,2u'+a,2v'+b]: a 4x4 stride-1
+        convolution of a 4C-channel image.  The parameter keeps the reference's [64, 3, 7, 7] shape (autograd carries
+        the weight gradient back through the rearrangement); one copy of the image and of the weight per call."""
+        n, c, h, w = x.shape
+        if h % 2 or w % 2:
+            return self.conv1(x)
+        cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+        xp = torch.nn.functional.pad(x, (3, 3, 3, 3))
+        hp, wp = (h + 6) // 2, (w + 6) // 2
+        wt = torch.nn.functional.pad(self.conv1.weight, (0, 1, 0, 1))
+        o = wt.shape[0]
+        if cl:      # build the NHWC memory order directly: [n, p, q, (c, a, b)]
+            xs = xp.view(n, c, hp, 2, wp, 2).permute(0, 2, 4, 1, 3, 5).reshape(n, hp, wp, 4 * c).permute(0, 3, 1, 2)
+            w4 = wt.view(o, c, 4, 2, 4, 2).permute(0, 2, 4, 1, 3, 5).reshape(o, 4, 4, 4 * c).permute(0, 3, 1, 2)
+        else:
+            xs = xp.view(n, c, hp, 2, wp, 2).permute(0, 1, 3, 5, 2, 4).reshape(n, 4 * c, hp, wp)
+            w4 = wt.view(o, c, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(o, 4 * c, 4, 4)
+        return torch.nn.functional.conv2d(xs, w4)
+
     def _stem(self, x):
+        if self.stem_s2d:
+            return self._stem_s2d(x)
         if self.stem_nchw:
             return self.conv1(x.contiguous()).contiguous(memory_format=torch.channels_last)
         if not self.stem_pad or x.shape[1] >= self.stem_pad:
@@ -219,13 +250,13 @@ class ResNet50DWT(_SiteOwner):
 
 
 def build_resnet50_dwt(state_dict, layers, site_mode="modules", num_classes=65, channels_last=False, stem_pad=0,
-                       stem_nchw=False):
+                       stem_nchw=False, stem_s2d=False):
     """state_dict uses the reference checkpoint's key names *without* the 7-char
     ``module.`` prefix (resnet50_dwt_mec_officehome.py:370-376).  channels_last=True converts the
     convolution weights to torch.channels_last so that, fed channels-last images, every activation
     stays NHWC (no cuDNN NCHW<->NHWC copies); results are identical, only strides change."""
     model = ResNet50DWT(layers, state_dict, num_classes=num_classes, site_mode=site_mode, stem_pad=stem_pad,
-                        stem_nchw=stem_nchw and channels_last)
+                        stem_nchw=stem_nchw and channels_last, stem_s2d=stem_s2d)
     model.load_state_dict(state_dict, strict=False)
     if channels_last and hasattr(layers, "MaxPool2d"):
         model.maxpool = layers.MaxPool2d(3, stride=2, padding=1)    # the library's channels-last kernel pair (no state)

@@ -191,8 +191,9 @@ def test_tensor_core_path_ill_conditioned(name, case, cond, scale, mos, dev):
 
 
 # --------------------------------------------------------------------------- whole model at the real site shapes
-@pytest.mark.parametrize("fmt,site_mode", [("nchw", "modules"), ("nchw", "fused"), ("nhwc", "fused")])
-def test_resnet_224_vs_reference_golden(fmt, site_mode, dev):
+@pytest.mark.parametrize("fmt,site_mode,stem", [("nchw", "modules", "direct"), ("nchw", "fused", "direct"), ("nhwc", "fused", "direct"),
+                                                ("nhwc", "fused", "s2d"), ("nchw", "fused", "s2d")])
+def test_resnet_224_vs_reference_golden(fmt, site_mode, stem, dev):
     """Harness model + CUDA layers vs the UNMODIFIED reference ResNet (CPU fp32, tests/golden/make_golden.py) on
     3 x 4 images of 224 x 224: the site shapes of BASELINE configs[2] (stem 64 x 112^2 ... layer4 2048 x 7^2)."""
     import torch.nn.functional as Fn
@@ -207,7 +208,8 @@ def test_resnet_224_vs_reference_golden(fmt, site_mode, dev):
     cl = fmt == "nhwc"
     if cl:
         x = x.contiguous(memory_format=torch.channels_last)
-    model = build_resnet50_dwt(sd, dwt_b200, site_mode=site_mode, channels_last=cl).to(dev).train()
+    # stem = "s2d": the 7x7 / 2 stem convolution evaluated as a 4x4 / 1 convolution of the space-to-depth image (harness option)
+    model = build_resnet50_dwt(sd, dwt_b200, site_mode=site_mode, channels_last=cl, stem_s2d=stem == "s2d").to(dev).train()
     logits = model(x)
     s, tt, a = torch.split(logits, logits.shape[0] // 3, dim=0)
     cls = Fn.nll_loss(Fn.log_softmax(s, dim=1), labels)
@@ -232,7 +234,7 @@ def test_resnet_224_vs_reference_golden(fmt, site_mode, dev):
     model.eval()
     with torch.no_grad():
         e["logits_eval"] = both(n(model(x)), z["logits_eval"])
-    print(fmt, site_mode, {k: ("%.2e" % v[0], "%.2e" % v[1]) for k, v in e.items()})
+    print(fmt, site_mode, stem, {k: ("%.2e" % v[0], "%.2e" % v[1]) for k, v in e.items()})
     # measured on B200: 2e-5 norm-wise / 3e-5 max-elementwise in all three builds (the ATen restatement: the same)
     assert e["logits"][0] < 2e-4 and e["logits"][1] < 5e-4, e["logits"]
     assert abs(cls.item() - float(z["cls_loss"])) < 2e-3 and abs(mec.item() - float(z["mec_loss"])) < 2e-3

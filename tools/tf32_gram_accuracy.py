@@ -1,7 +1,9 @@
 """CPU emulation of the tf32 Gram contraction of the forward statistics (csrc/norm_tc.cu): covariance and y error of
 
   single   G = sum RN_tf32(s) RN_tf32(s)^T                        (round-1 kernel: one tf32 pass)
-  split    G = HH + LH + LH^T,  hi = trunc_tf32(s), lo = RN_tf32(s - hi)   (round-2 tc_gram_kernel)
+  split    G = HH + LH + LH^T,  hi = trunc_tf32(s), lo = trunc_tf32(s - hi): the shipped tc_gram_kernel -- the tensor
+           core reads the top 19 bits of the fp32 words it is handed (s itself for hi, s - trunc(s) for lo)
+  split-rn the same with hi = RN_tf32(s) (the first round-2 kernel: two more instructions per element)
   fp32     the same sums with fp32 operands                        (what the reference's torch.bmm computes)
 
 against the fp64 covariance, over condition number, activation scale and |mean|/sigma.  s = x - K with the pilot
@@ -53,9 +55,11 @@ def run(M, gs=64, cond=1e2, scale=1.0, mos=2.0, seed=0, rz=False):
     xc = x - x.mean(1, keepdims=True)
     y64 = w(exact) @ xc
     hi = tr(xs)
-    lo = rn(xs - hi)
-    lh = acc(lo, hi, rz)
-    grams = {"single": acc(rn(xs), rn(xs), rz), "split": acc(hi, hi, rz) + lh + lh.T, "fp32": acc(xs, xs, False)}
+    lh = acc(tr(xs - hi), hi, rz)
+    hr = rn(xs)
+    lhr = acc(tr(xs - hr), hr, rz)
+    grams = {"single": acc(rn(xs), rn(xs), rz), "split": acc(hi, hi, rz) + lh + lh.T,
+             "split-rn": acc(hr, hr, rz) + lhr + lhr.T, "fp32": acc(xs, xs, False)}
     out = {}
     for name, g in grams.items():
         c = g / M - s1 @ s1.T
@@ -63,11 +67,14 @@ def run(M, gs=64, cond=1e2, scale=1.0, mos=2.0, seed=0, rz=False):
     return out
 
 
+NAMES = ("single", "split", "split-rn", "fp32")
+
+
 if __name__ == "__main__":
     rz = "--rz" in sys.argv
     M = 4704 if rz else 65536
     print(f"M = {M}, gs = 64, eps = 1e-3" + (", truncating fp32 accumulator per 8-sample step" if rz else ""))
-    print(f"{'cond':>6} {'scale':>6} {'|mu|/sd':>8} | " + " | ".join(f"{n + ' cov':>11} {n + ' y':>10}" for n in ("single", "split", "fp32")))
+    print(f"{'cond':>6} {'scale':>6} {'|mu|/sd':>8} | " + " | ".join(f"{n + ' cov':>11} {n + ' y':>10}" for n in NAMES))
     for cond, scale, mos in [(1e2, 1, 2), (1e3, 10, 0), (1e4, 30, 0), (1e4, 100, 0), (1e1, 1, 50), (1e3, 10, 50)]:
         r = run(M, cond=cond, scale=scale, mos=mos, rz=rz)
-        print(f"{cond:6.0e} {scale:6.0f} {mos:8.0f} | " + " | ".join(f"{r[n][0]:11.2e} {r[n][1]:10.2e}" for n in ("single", "split", "fp32")))
+        print(f"{cond:6.0e} {scale:6.0f} {mos:8.0f} | " + " | ".join(f"{r[n][0]:11.2e} {r[n][1]:10.2e}" for n in NAMES))
