@@ -11,7 +11,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdwt_b200.so")
+# DWT_B200_LIB: another build of the same library (development: A/B timing of a kernel variant on one box)
+LIB_PATH = os.environ.get("DWT_B200_LIB") or os.path.join(_HERE, "lib", "libdwt_b200.so")
 
 ABI_VERSION = 4
 MAX_DOMAINS = 4

@@ -39,6 +39,9 @@
 //
 // Reference: utils/whitening.py:46-47 (/root/reference) and its autograd transpose.
 #include <cuda.h>
+#ifdef DWT_PROF_GRAM
+#include <cstdio>
+#endif
 
 #include "dwt_common.cuh"
 #include "norm_launch.h"
@@ -352,6 +355,14 @@ struct GramBarriers {
 // tile paced the round-1 single-pass kernel) -- profiles/ncu_r02_tc_gram.md.
 constexpr int kGramThreads = kTcThreads + 32;
 
+// development: -DDWT_PROF_GRAM records a clock64 timeline of tiles kProfT0.. of CTA (0, 0, 0) and prints it
+#ifdef DWT_PROF_GRAM
+constexpr int kProfT0 = 96, kProfN = 48;
+#define GPROF(ev, it) do { if (prof_on && (it) >= kProfT0 && (it) < kProfT0 + kProfN) sProf[ev][(it) - kProfT0] = clock64(); } while (0)
+#else
+#define GPROF(ev, it)
+#endif
+
 __global__ void __launch_bounds__(kGramThreads, 2)
 tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restrict__ x, const Geom gm,
                float* __restrict__ shift_out, float* __restrict__ partial) {
@@ -363,6 +374,10 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
   __shared__ float sRS[kTileCh];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const int sb = blockIdx.y, d = blockIdx.z, ch0 = sb * kTileCh;
+#ifdef DWT_PROF_GRAM
+  __shared__ long long sProf[6][kProfN];
+  const bool prof_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+#endif
   const TileRange tr(gm);
   const int ntiles = tr.end - tr.begin;
 
@@ -414,6 +429,7 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
         const int s = it % STAGES;
         uint64_t* full = &bars.full[it % (2 * STAGES)];
         mbar_wait_relaxed(&bars.empty[s], ((it / STAGES) & 1) ^ 1);
+        GPROF(0, it);
         mbar_arrive_expect_tx(full, kTileBytes);
         tma_load_3d(smem + (size_t)s * kGramStageBytes, &map_x, pb * kTilePx, ch0, d * gm.N + n, full);
         if (++pb == tr.PB) { pb = 0; ++n; }
@@ -427,6 +443,7 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
     const uint32_t dacc = tmem_d + (uint32_t)(m * kGramN);
     for (int it = m; it < ntiles; it += 2) {
       mbar_wait(&bars.ready[it % (2 * STAGES)], (it / (2 * STAGES)) & 1);
+      GPROF(4, it);
       tc_fence_after();
       if (lane == 0) {
         const int s = it % STAGES, a = it % NA;
@@ -437,6 +454,7 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
         umma_commit(&bars.empty[s]);
         umma_commit(&bars.a_empty[it % (2 * NA)]);
         if (it + 2 >= ntiles) umma_commit(&bars.accum[m]);
+        GPROF(5, it);
       }
       __syncwarp();
     }
@@ -450,7 +468,9 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
     for (int it = set; it < ntiles; it += 2) {
       const int s = it % STAGES, a = it % NA, u = it - NA;                // u: the tile that used A slot a before
       mbar_wait(&bars.full[it % (2 * STAGES)], (it / (2 * STAGES)) & 1);
+      if (quad == 0) GPROF(1, it);
       if (u >= 0) mbar_wait(&bars.a_empty[u % (2 * NA)], (u / (2 * NA)) & 1);
+      if (quad == 0) GPROF(2, it);
       tc_fence_after();
       const uint32_t tile = smem0 + (uint32_t)(s * kGramStageBytes), ta = ta0 + (uint32_t)(a * kTilePx);
       gram_transform_quarter(tile, row, !lo_lane, lo_lane ? 0xFFFFE000u : 0u, shift, pb * kTilePx, gm.HW, rowok, ta);
@@ -458,6 +478,7 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.ready[it % (2 * STAGES)]);
+      if (quad == 0) GPROF(3, it);
       pb += 2;
       while (pb >= tr.PB) { pb -= tr.PB; ++n; }
     }
@@ -520,6 +541,15 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc<kGramTmemCols>(tmem); }
+#ifdef DWT_PROF_GRAM
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && ntiles >= kProfT0 + kProfN) {
+    const long long t0 = sProf[0][0];
+    printf("tc_gram timeline (cycles from the TMA issue of tile %d): tile | tma full a_free arrive | ready issued\n", kProfT0);
+    for (int i = 0; i < kProfN; ++i)
+      printf("%3d %7lld %7lld %7lld %7lld %7lld %7lld\n", kProfT0 + i, sProf[0][i] - t0, sProf[1][i] - t0, sProf[2][i] - t0,
+             sProf[3][i] - t0, sProf[4][i] - t0, sProf[5][i] - t0);
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

@@ -5,8 +5,8 @@ import csv, re, sys, collections
 
 def family(name):
     n = name
-    if "dwt" in n or "cl_" in n or "tc_" in n or "small_" in n or "tiled_" in n or "vec_reduce" in n or "head_loss" in n or "mec_kernel" in n or "fwd_factor" in n or "bwd_coef" in n or "partial_reduce" in n or "augment" in n:
-        m = re.search(r"(cl_[a-z_]+?|tc_[a-z_]+?|small_[a-z_]+?|tiled_[a-z_]+?|vec_reduce|head_loss|mec|fwd_factor|bwd_coef|partial_reduce|augment_pair)_kernel", n)
+    if "dwt::" in n:
+        m = re.search(r"(cl_[a-z_]+?|tc_[a-z_]+?|small_[a-z_]+?|tiled_[a-z_]+?|vec_reduce|head_loss|mec|fwd_factor|bwd_coef|partial_reduce|augment_pair|maxpool_[a-z]+)_kernel", n)
         return "dwt_b200: " + (m.group(1) if m else n[:40])
     low = n.lower()
     if "nchwtonhwc" in low or "nhwctonchw" in low: return "cuDNN layout conversion"
