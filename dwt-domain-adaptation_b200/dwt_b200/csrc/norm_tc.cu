@@ -192,10 +192,10 @@ tc_contract_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const int s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(&bars.ready[s], ph);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t xaddr = smem_u32(smem + (size_t)s * NT * kTileBytes);
-        const uint64_t xdesc = make_kmajor_sw128_desc(xaddr);
-        const uint64_t adesc = TWO ? make_kmajor_sw128_desc(xaddr + kTileBytes) : xdesc;   // A = dy tile (rows i)
+      const uint32_t xaddr = smem_u32(smem + (size_t)s * NT * kTileBytes);      // warp-uniform; one elected lane issues
+      const uint64_t xdesc = make_kmajor_sw128_desc(xaddr);
+      const uint64_t adesc = TWO ? make_kmajor_sw128_desc(xaddr + kTileBytes) : xdesc;   // A = dy tile (rows i)
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kTilePx / 8; ++k)
           umma_tf32(tmem_d, adesc + 2 * k, xdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
@@ -445,15 +445,19 @@ tc_gram_kernel(const __grid_constant__ CUtensorMap map_x, const float* __restric
       mbar_wait(&bars.ready[it % (2 * STAGES)], (it / (2 * STAGES)) & 1);
       GPROF(4, it);
       tc_fence_after();
-      if (lane == 0) {
-        const int s = it % STAGES, a = it % NA;
-        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + (size_t)s * kGramStageBytes));
+      const int s = it % STAGES, a = it % NA;                 // warp-uniform: computed by every lane, issued by one
+      const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + (size_t)s * kGramStageBytes));
+      const uint32_t ta = tmem_a0 + (uint32_t)(a * kTilePx);
+      uint64_t* e_stage = &bars.empty[s];
+      uint64_t* e_slot = &bars.a_empty[it % (2 * NA)];
+      const bool last = it + 2 >= ntiles;
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kTilePx / 8; ++k)
-          umma_tf32_ts(dacc, tmem_a0 + (uint32_t)(a * kTilePx + 8 * k), bdesc + 2 * k, idesc, (it >= 2 || k > 0) ? 1u : 0u);
-        umma_commit(&bars.empty[s]);
-        umma_commit(&bars.a_empty[it % (2 * NA)]);
-        if (it + 2 >= ntiles) umma_commit(&bars.accum[m]);
+          umma_tf32_ts(dacc, ta + (uint32_t)(8 * k), bdesc + 2 * k, idesc, (it >= 2 || k > 0) ? 1u : 0u);
+        umma_commit(e_stage);
+        umma_commit(e_slot);
+        if (last) umma_commit(&bars.accum[m]);
         GPROF(5, it);
       }
       __syncwarp();

@@ -222,8 +222,10 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         mbar_wait(&bars.full[r], (st / RAW) & 1);             // already complete (the transform warps waited on it)
         mbar_wait(&bars.ready[l], (st / kLo) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t raw = smem_u32(sRaw + (size_t)r * SLOT), lo = smem_u32(sLo + (size_t)l * SLOT);
+        // operands are warp-uniform and computed by every lane; ONE elected lane issues (tc_ptx.cuh elect_one: without it
+        // the compiler wrapped every tcgen05 instruction in its own election loop with four register-to-uniform moves)
+        const uint32_t raw = smem_u32(sRaw + (size_t)r * SLOT), lo = smem_u32(sLo + (size_t)l * SLOT);
+        if (elect_one()) {
 #pragma unroll
           for (int term = 0; term < 2; ++term) {                 // B = raw tile (hi by truncation), then lo
             const uint32_t bbase = term == 0 ? raw : lo;
