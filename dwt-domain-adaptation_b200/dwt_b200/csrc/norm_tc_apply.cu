@@ -42,6 +42,7 @@
 //
 // Reference: the grouped 1x1 convolution at utils/whitening.py:55 (/root/reference) and its backward.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "dwt_common.cuh"
 #include "norm_launch.h"
@@ -83,6 +84,12 @@ struct ApBarriers {
   uint32_t tmem_slot;
 };
 
+// DWT_TC_INTERLEAVE=0/1 (development): tile order of the apply kernels
+inline int tile_interleave() {
+  static const int v = [] { const char* e = getenv("DWT_TC_INTERLEAVE"); return (e && e[0] == '1') ? 1 : 0; }();
+  return v;
+}
+
 struct ApplyArgs {
   const float* mats;      // per (domain, group) records
   int rec_stride;         // floats per record
@@ -90,6 +97,7 @@ struct ApplyArgs {
   const float* shift[2];  // per-channel shift of input i
   int shift_stride[2];    // floats per domain in shift[i]
   float* out;
+  int interleave;         // 1: CTA b takes tiles b, b + grid, b + 2 grid, ... (neighbouring CTAs on neighbouring tiles)
 };
 
 // 128-bit shared-memory accesses with the state space spelled out: through a generic pointer these compile to
@@ -142,8 +150,11 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
   const int sb = blockIdx.y, d = blockIdx.z, ch0 = sb * kCh;
   const int PB = (gm.HW + TPX - 1) / TPX;
   const long long T = (long long)gm.N * PB;
-  const int t_begin = (int)(T * blockIdx.x / gridDim.x), t_end = (int)(T * (blockIdx.x + 1) / gridDim.x);
-  const int ntiles = t_end - t_begin;
+  // tile of step `it`: a contiguous range per CTA, or (interleave) the CTAs of a super-block walk the tensor side by side
+  const int t_step = args.interleave ? (int)gridDim.x : 1;
+  const int t_begin = args.interleave ? (int)blockIdx.x : (int)(T * blockIdx.x / gridDim.x);
+  const int ntiles = args.interleave ? (int)((T - blockIdx.x + gridDim.x - 1) / gridDim.x)
+                                     : (int)(T * (blockIdx.x + 1) / gridDim.x) - t_begin;
 
   if (tid == 0) {
     for (int r = 0; r < RAW; ++r) { mbar_init(&bars.full[r], 1); mbar_init(&bars.raw_empty[r], 1); }
@@ -194,7 +205,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
     // ===== TMA producer =====
     if (lane == 0) {
       for (int it = 0; it < ntiles; ++it) {
-        const int t = t_begin + it, n = t / PB, pb = t - n * PB;
+        const int t = t_begin + it * t_step, n = t / PB, pb = t - n * PB;
         // 32-pixel boxes of the tile that lie entirely past the row end are not issued (their columns are never
         // stored, whatever the stale shared memory holds)
         int nbox = (gm.HW - pb * TPX + kBoxPx - 1) / kBoxPx;
@@ -284,7 +295,7 @@ tc_apply_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant_
         const float send = upper ? v[c] : v[KEEP + c];
         o[c] = (keep + __shfl_xor_sync(0xffffffffu, send, 16)) - rconst;
       }
-      const int t = t_begin + e, n = t / PB, pb = t - n * PB;
+      const int t = t_begin + e * t_step, n = t / PB, pb = t - n * PB;
       const int px = pb * TPX + part * WC + (upper ? KEEP : 0);
       if (ch < gm.C) {
         float* orow = args.out + ((size_t)(d * gm.N + n) * gm.C + ch) * gm.HW + px;
@@ -351,6 +362,7 @@ int tc_apply(const float* x, float* y, const Geom& gm, int nctas, const float* s
   bind_context();
   if (int rc = make_map_ap(&mx, x, gm)) return rc;
   ApplyArgs a{};
+  a.interleave = tile_interleave();
   a.mats = save_w; a.rec_stride = gm.GS * gm.GS; a.off[0] = 0; a.off[1] = 0;
   a.shift[0] = save_mean; a.shift_stride[0] = gm.C; a.shift[1] = nullptr; a.shift_stride[1] = 0;
   a.out = y;
@@ -367,6 +379,7 @@ int tc_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, i
   if (int rc = make_map_ap(&mg, dout, gm)) return rc;
   if (int rc = make_map_ap(&mx, x, gm)) return rc;
   ApplyArgs a{};
+  a.interleave = tile_interleave();
   a.mats = coef; a.rec_stride = coef_stride(gm.GS); a.off[0] = 0; a.off[1] = gm.GS * gm.GS;
   a.shift[0] = dybar; a.shift_stride[0] = ((gm.C + kCh - 1) / kCh) * kCh;
   a.shift[1] = save_mean; a.shift_stride[1] = gm.C;
