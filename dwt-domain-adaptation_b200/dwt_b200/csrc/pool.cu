@@ -9,7 +9,8 @@
 //             float4 loads (a warp covers whole pixels: C/4 consecutive float4), max with ATen's rule (strict >, NaN wins, first maximum
 //             in row-major window order keeps the index), one float4 store + 4 index BYTES (window-local k*k index);
 //   backward  one CTA per input row, one thread per INPUT float4: the <= ceil(k/s)^2 windows that contain the pixel
-//             are visited, and a window's gradient is taken iff its saved index names this pixel.
+//             are visited, and a window's gradient is taken iff its saved index names this pixel; the stem geometry
+//             (3 x 3 / 2 / 1, even H and W) has its own kernel: one thread per 2 x 2 input patch, all loads up front.
 // Algorithmic bytes: forward 4*(in + out) + out, backward 4*(in + out) + out  (in, out = element counts).
 //
 // Semantics = torch.nn.functional.max_pool2d(x, k, s, p) (dilation 1, ceil_mode False) and its autograd, bit for bit
@@ -112,6 +113,52 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
   }
 }
 
+// Backward of the ResNet stem pool (3 x 3, stride 2, pad 1, even H and W, C/4 a power of two): one thread per 2 x 2 INPUT
+// patch and channel quad.  The patch (rows 2k, 2k+1; columns 2j, 2j+1) is touched by exactly the four windows
+// (k + a, j + b), a, b in {0, 1}: their 4 index words and 4 gradient float4 are loaded up front (8 independent loads in
+// flight per thread instead of a dependent index -> compare -> gradient chain per input element; the gradient tensor is a
+// quarter of the input and stays in L2), then the four outputs are composed with the same ascending (oh, ow) summation
+// order as the generic kernel.  Window-local codes kh * 3 + kw:
+//   (2k, 2j):     w00 code 4                      (2k, 2j+1):   w00 code 5, w01 code 3
+//   (2k+1, 2j):   w00 code 7, w10 code 1          (2k+1, 2j+1): w00 code 8, w01 code 6, w10 code 2, w11 code 0
+__device__ __forceinline__ void take(float4& acc, const float4& gq, uint32_t m, unsigned code) {
+  if ((m & 0xFFu) == code) acc.x += gq.x;
+  if (((m >> 8) & 0xFFu) == code) acc.y += gq.y;
+  if (((m >> 16) & 0xFFu) == code) acc.z += gq.z;
+  if ((m >> 24) == code) acc.w += gq.w;
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_3s2_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                                              float* __restrict__ dx, const PoolGeom g) {
+  const int H2 = g.H >> 1, W2 = g.W >> 1;
+  const int n = blockIdx.y / H2, k = blockIdx.y - n * H2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W2 * g.C4) return;
+  const int j = i >> g.c4shift, c4 = i & (g.C4 - 1);
+  const float4* dyn = reinterpret_cast<const float4*>(dy) + (size_t)n * g.OH * g.OW * g.C4;
+  const uint32_t* ixn = reinterpret_cast<const uint32_t*>(idx) + (size_t)n * g.OH * g.OW * g.C4;
+  uint32_t m[2][2];
+  float4 gq[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const bool ok = (k + a < g.OH) && (j + b < g.OW);
+      const size_t o = ((size_t)(k + a) * g.OW + (j + b)) * g.C4 + c4;
+      m[a][b] = ok ? __ldg(ixn + o) : 0xFFFFFFFFu;          // 0xFF matches no code
+      gq[a][b] = ok ? __ldg(dyn + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  float4 o00 = make_float4(0.f, 0.f, 0.f, 0.f), o01 = o00, o10 = o00, o11 = o00;
+  take(o00, gq[0][0], m[0][0], 4u);
+  take(o01, gq[0][0], m[0][0], 5u); take(o01, gq[0][1], m[0][1], 3u);
+  take(o10, gq[0][0], m[0][0], 7u); take(o10, gq[1][0], m[1][0], 1u);
+  take(o11, gq[0][0], m[0][0], 8u); take(o11, gq[0][1], m[0][1], 6u); take(o11, gq[1][0], m[1][0], 2u); take(o11, gq[1][1], m[1][1], 0u);
+  float4* r0 = reinterpret_cast<float4*>(dx) + (((size_t)n * g.H + 2 * k) * g.W + 2 * j) * g.C4 + c4;
+  float4* r1 = r0 + (size_t)g.W * g.C4;
+  r0[0] = o00; r0[g.C4] = o01;
+  r1[0] = o10; r1[g.C4] = o11;
+}
+
 }  // namespace
 
 namespace {
@@ -134,7 +181,10 @@ void maxpool_bwd_launch(const float* dy, const uint8_t* idx, float* dx, int N, i
                         int p, cudaStream_t st) {
   const int sh = pow2_shift(C / 4);
   const PoolGeom g{N, H, W, C / 4, OH, OW, k, s, p, sh < 0 ? 0 : sh};
-  if (k == 3 && s == 2 && p == 1 && sh >= 0) maxpool_bwd_kernel<3, 2, 1, true><<<N * H, 256, 0, st>>>(dy, idx, dx, g);
+  if (k == 3 && s == 2 && p == 1 && sh >= 0 && H % 2 == 0 && W % 2 == 0 && (long long)N * (H / 2) <= 65535) {
+    const int items = (W / 2) * (C / 4), threads = items >= 256 ? 256 : ((items + 31) / 32) * 32;
+    maxpool_bwd_3s2_kernel<<<dim3((items + threads - 1) / threads, N * (H / 2)), threads, 0, st>>>(dy, idx, dx, g);
+  } else if (k == 3 && s == 2 && p == 1 && sh >= 0) maxpool_bwd_kernel<3, 2, 1, true><<<N * H, 256, 0, st>>>(dy, idx, dx, g);
   else maxpool_bwd_kernel<0, 0, 0, false><<<N * H, 256, 0, st>>>(dy, idx, dx, g);
 }
 
