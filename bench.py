@@ -526,6 +526,11 @@ def run_ours(args):
     nhwc = args.memory_format == "nhwc"
     model = build_model(dwt_b200, device, args.site_mode, channels_last=nhwc, stem_pad=args.stem_pad, stem_nchw=args.stem_nchw,
                         stem_s2d=args.stem == "s2d")
+    if not args.grad_fork:                                      # experiment: let autograd add the two gradients of a block input
+        from harness.resnet50_dwt import Bottleneck
+        for m in model.modules():
+            if isinstance(m, Bottleneck):
+                object.__setattr__(m, "_fork", None)
     net = model
     sync = FlatGradAllReduce(model, world, segments=args.grad_segments, gather=args.grad_gather) if distributed else None   # one GPU: plain .grad tensors
     opt = make_optimizer(model)
@@ -850,6 +855,8 @@ def main():
     ap.add_argument("--sites-out", default="", help="write the per-site kernel table (JSON) here")
     ap.add_argument("--stem-pad", type=int, default=0, choices=[0, 4, 8],
                     help="zero-pad the 3-channel image (and the stem weight) to this many channels for cuDNN")
+    ap.add_argument("--no-grad-fork", dest="grad_fork", action="store_false",
+                    help="sum the two gradients of every block input with autograd's add instead of inside the site's backward kernels")
     ap.add_argument("--stem", default=DEFAULT_STEM, choices=["direct", "s2d"],
                     help="s2d: the 7x7/2 stem convolution as a 4x4/1 convolution of the 2x2 space-to-depth image (same arithmetic)")
     ap.add_argument("--stem-nchw", action="store_true", help="run only the 3-channel stem convolution in NCHW (experiment)")

@@ -9,10 +9,11 @@ from ._native import NotPositiveDefiniteError, check_status, raise_on_status
 from .augment import PairedAugment, draw_params
 from .batch_norm import BatchNorm1d, BatchNorm2d, BatchNorm3d
 from .consensus_loss import HeadLoss, MinEntropyConsensusLoss
+from .functional import fork_for_sum
 from .fused import DomainTripleNorm
 from .pooling import MaxPool2d
 from .whitening import WTransform2d
 
 __all__ = ["WTransform2d", "BatchNorm1d", "BatchNorm2d", "BatchNorm3d", "MinEntropyConsensusLoss",
-           "DomainTripleNorm", "HeadLoss", "MaxPool2d", "PairedAugment", "draw_params", "raise_on_status", "check_status",
+           "DomainTripleNorm", "fork_for_sum", "HeadLoss", "MaxPool2d", "PairedAugment", "draw_params", "raise_on_status", "check_status",
            "NotPositiveDefiniteError", "_native"]

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DWT_B200_LIB: another build of the same library (development: A/B timing of a kernel variant on one box)
 LIB_PATH = os.environ.get("DWT_B200_LIB") or os.path.join(_HERE, "lib", "libdwt_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_DOMAINS = 4
 MAX_GROUP_SIZE = 64
 MODE_TRAIN, MODE_EVAL = 0, 1
@@ -34,7 +34,7 @@ _SIGNATURES = {
                                       ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
                                       _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_int, _c_float_p,
                                       _c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
-    "dwt_whiten_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64,
+    "dwt_whiten_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                       _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p, _c_float_p,
                                       ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_size_t,
@@ -44,7 +44,7 @@ _SIGNATURES = {
                                   ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), _c_float_p,
                                   _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_int, _c_float_p, _c_float_p,
                                   ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
-    "dwt_bn_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+    "dwt_bn_bwd": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                   ctypes.c_int, ctypes.c_int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                   ctypes.c_void_p, _c_float_p, ctypes.c_int, _c_float_p, _c_float_p, ctypes.c_void_p,
                                   ctypes.c_size_t, ctypes.c_void_p]),

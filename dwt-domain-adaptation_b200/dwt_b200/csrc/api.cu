@@ -391,7 +391,7 @@ int whiten_like_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, 
   return check_launch("whitening apply kernel");
 }
 
-int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int64_t C, int64_t HW, int GS, int D,
+int whiten_like_bwd(const float* x, const float* dout, const float* dout2, float* dx, int64_t N, int64_t C, int64_t HW, int GS, int D,
                     int mode, float a, const float* save_mean, const float* save_w, const float* gamma,
                     const float* beta, const uint8_t* relu_mask, float* dresidual, int epi, float* dgamma,
                     float* dbeta, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -400,6 +400,9 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
   Plan p;
   if (int rc = make_plan(p, K_BWD_REDUCE, K_BWD_APPLY, x, dout, dx, N, C, HW, GS, D)) return rc;
   if (!x || !dout || !dx || !save_mean || !save_w || !ws) return fail(DWT_E_INVALID, "null pointer argument");
+  if (dout2 && (!nhwc || (uintptr_t)dout2 % 16 != 0))
+    return fail(nhwc ? DWT_E_INVALID : DWT_E_UNSUPPORTED, "a second gradient addend (dout2) is built for the channels-last "
+                "kernels (16-byte aligned tensor); add it to dout otherwise");
   if (nhwc && !dwt::cl_supports((int)C, GS))
     return fail(DWT_E_UNSUPPORTED, "channels-last layout is built for group_size 1, 2, 4 with C/4 a power of two (C=%lld gs=%d)", (long long)C, GS);
   if (nhwc && (((uintptr_t)x | (uintptr_t)dout | (uintptr_t)dx) % 16 != 0)) return fail(DWT_E_INVALID, "channels-last tensors must be 16-byte aligned");
@@ -438,8 +441,8 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
     const bool masked = (epi & DWT_EPI_RESIDUAL) != 0;
     if (need_reduce) {
       {
-        Launch l("cl_bwd_reduce", &p.gm, (masked ? 2.0625 : 2.0) * E, st);
-        dwt::cl_bwd_reduce(x, dout, p.gm, cp.nred, cp.gz_red, epi, save_mean, save_w, gamma, beta, relu_mask, w.partial, st);
+        Launch l("cl_bwd_reduce", &p.gm, ((masked ? 2.0625 : 2.0) + (dout2 ? 1.0 : 0.0)) * E, st);
+        dwt::cl_bwd_reduce(x, dout, dout2, p.gm, cp.nred, cp.gz_red, epi, save_mean, save_w, gamma, beta, relu_mask, w.partial, st);
       }
       if (int rc = check_launch("channels-last backward reduction kernel")) return rc;
       Launch l("cl_bwd_finalize", &p.gm, 0.0, st);
@@ -450,8 +453,8 @@ int whiten_like_bwd(const float* x, const float* dout, float* dx, int64_t N, int
     }
     if (int rc = check_launch("channels-last backward finalize kernel")) return rc;
     {
-      Launch l("cl_bwd_apply", &p.gm, (masked ? (dresidual ? 4.0625 : 3.0625) : 3.0) * E, st);
-      dwt::cl_bwd_apply(x, dout, dx, p.gm, cp.new_, cp.gz_ew, epi, w.coef, save_mean, save_w, gamma, beta, relu_mask, dresidual, st);
+      Launch l("cl_bwd_apply", &p.gm, ((masked ? (dresidual ? 4.0625 : 3.0625) : 3.0) + (dout2 ? 1.0 : 0.0)) * E, st);
+      dwt::cl_bwd_apply(x, dout, dout2, dx, p.gm, cp.new_, cp.gz_ew, epi, w.coef, save_mean, save_w, gamma, beta, relu_mask, dresidual, st);
     }
     return check_launch("channels-last backward apply kernel");
   }
@@ -513,11 +516,11 @@ int dwt_whiten_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, i
                          workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int dwt_whiten_bwd(const float* x, const float* dout, float* dx, int64_t N, int64_t C, int64_t HW, int group_size,
+int dwt_whiten_bwd(const float* x, const float* dout, const float* dout2, float* dx, int64_t N, int64_t C, int64_t HW, int group_size,
                    int n_domains, int mode, float eps, const float* save_mean, const float* save_w,
                    const float* gamma, const float* beta, const uint8_t* relu_mask, float* dresidual, int epilogue,
                    float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, dwt_stream_t stream) {
-  return whiten_like_bwd(x, dout, dx, N, C, HW, group_size, n_domains, mode, 1.f - eps, save_mean, save_w, gamma,
+  return whiten_like_bwd(x, dout, dout2, dx, N, C, HW, group_size, n_domains, mode, 1.f - eps, save_mean, save_w, gamma,
                          beta, relu_mask, dresidual, epilogue, dgamma, dbeta, workspace, workspace_bytes,
                          (cudaStream_t)stream);
 }
@@ -535,11 +538,11 @@ int dwt_bn_fwd(const float* x, float* y, int64_t N, int64_t C, int64_t HW, int n
                          workspace_bytes, (cudaStream_t)stream);
 }
 
-int dwt_bn_bwd(const float* x, const float* dout, float* dx, int64_t N, int64_t C, int64_t HW, int n_domains,
+int dwt_bn_bwd(const float* x, const float* dout, const float* dout2, float* dx, int64_t N, int64_t C, int64_t HW, int n_domains,
                int mode, const float* save_mean, const float* save_invstd, const float* weight, const float* bias,
                const uint8_t* relu_mask, float* dresidual, int epilogue, float* dweight, float* dbias, void* workspace,
                size_t workspace_bytes, dwt_stream_t stream) {
-  return whiten_like_bwd(x, dout, dx, N, C, HW, 1, n_domains, mode, 1.f, save_mean, save_invstd, weight, bias,
+  return whiten_like_bwd(x, dout, dout2, dx, N, C, HW, 1, n_domains, mode, 1.f, save_mean, save_invstd, weight, bias,
                          relu_mask, dresidual, epilogue, dweight, dbias, workspace, workspace_bytes,
                          (cudaStream_t)stream);
 }

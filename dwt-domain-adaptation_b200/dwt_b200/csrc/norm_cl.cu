@@ -378,8 +378,8 @@ __global__ void __launch_bounds__(kT, 3) cl_apply_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------
 // backward reduce: partial[d][cta][q][BWD]  (per problem: R row-major, then sdz)
 // ------------------------------------------------------------------------------------------
-template <int GS, int EPI>
-__global__ void __launch_bounds__(kT, 2) cl_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dout,
+template <int GS, int EPI, bool D2>
+__global__ void __launch_bounds__(kT, 2) cl_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dout, const float* __restrict__ dout2,
                                                               const Geom gm, const float* __restrict__ save_mean,
                                                               const float* __restrict__ save_w, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const uint8_t* __restrict__ mask,
@@ -411,20 +411,27 @@ __global__ void __launch_bounds__(kT, 2) cl_bwd_reduce_kernel(const float* __res
     const size_t base = (size_t)d * rows * gm.C + 4 * t.q;
     const float* xd = x + base;
     const float* gd = dout + base;
+    const float* gd2 = D2 ? dout2 + base : nullptr;        // second addend of the incoming gradient (see dwt_b200.h)
     const uint8_t* md = mask + (size_t)d * rows * t.C4 + t.q;
     sweep_rows<UNROLL, true>(t, rows, [&](unsigned r) {
-      float4 v[UNROLL], q[UNROLL];
+      float4 v[UNROLL], q[UNROLL], q2[D2 ? UNROLL : 1];
       unsigned mb[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {                       // every load of the step first: nothing waits on another
         const unsigned rr = r + u * t.rpi;
         if (rr < rows) {
           v[u] = ldg4(xd + (size_t)rr * gm.C); q[u] = ldg4(gd + (size_t)rr * gm.C);
           if constexpr (MASK) mb[u] = __ldg(md + (size_t)rr * t.C4);
+          if constexpr (D2) q2[u] = ldg4(gd2 + (size_t)rr * gm.C);
         } else {
           v[u] = make_float4(mu[0], mu[1], mu[2], mu[3]); q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (MASK) mb[u] = 0u;
+          if constexpr (D2) q2[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      }
+      if constexpr (D2) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) { q[u].x += q2[u].x; q[u].y += q2[u].y; q[u].z += q2[u].z; q[u].w += q2[u].w; }
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
@@ -500,8 +507,8 @@ __global__ void __launch_bounds__(32 * kFinQ * DWT_MAX_DOMAINS) cl_bwd_finalize_
 // ------------------------------------------------------------------------------------------
 // backward apply
 // ------------------------------------------------------------------------------------------
-template <int GS, int EPI>
-__global__ void __launch_bounds__(kT, 2) cl_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dout,
+template <int GS, int EPI, bool D2>
+__global__ void __launch_bounds__(kT, 2) cl_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dout, const float* __restrict__ dout2,
                                                              float* __restrict__ dx, const Geom gm, const float* __restrict__ coef,
                                                              const float* __restrict__ save_mean, const float* __restrict__ save_w,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -535,11 +542,12 @@ __global__ void __launch_bounds__(kT, 2) cl_bwd_apply_kernel(const float* __rest
     const size_t base = (size_t)d * rows * gm.C + 4 * t.q;
     const float* xd = x + base;
     const float* gd = dout + base;
+    const float* gd2 = D2 ? dout2 + base : nullptr;        // second addend of the incoming gradient (see dwt_b200.h)
     float* od = dx + base;
     float* rd = dres + base;
     const uint8_t* md = mask + (size_t)d * rows * t.C4 + t.q;
     sweep_rows<UNROLL, false>(t, rows, [&](unsigned r) {
-      float4 v[UNROLL], q[UNROLL];
+      float4 v[UNROLL], q[UNROLL], q2[D2 ? UNROLL : 1];
       unsigned mb[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
@@ -547,7 +555,13 @@ __global__ void __launch_bounds__(kT, 2) cl_bwd_apply_kernel(const float* __rest
         if (rr < rows) {
           v[u] = ldg4(xd + (size_t)rr * gm.C); q[u] = ldg4(gd + (size_t)rr * gm.C);
           if constexpr (MASK) mb[u] = __ldg(md + (size_t)rr * t.C4);
+          if constexpr (D2) q2[u] = ldg4(gd2 + (size_t)rr * gm.C);
         }
+      }
+      if constexpr (D2) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          if (r + u * t.rpi < rows) { q[u].x += q2[u].x; q[u].y += q2[u].y; q[u].z += q2[u].z; q[u].w += q2[u].w; }
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
@@ -659,19 +673,25 @@ void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int gz, int e
   CL_GS(gm.GS, CL_EPI(epi, (launch_k(cl_apply_kernel<kGS, kEPI>, cl_grid(gm, nctas, gz), dim3(kT), st, use_pdl(), x, y, gm, mean, w, gamma, beta,
                                      (const float*)nullptr, (uint8_t*)nullptr))));
 }
-void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
+void cl_bwd_reduce(const float* x, const float* dout, const float* dout2, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
                    const float* gamma, const float* beta, const uint8_t* mask, float* partial, cudaStream_t st) {
-  CL_GS(gm.GS, CL_EPI_BWD(epi, (cl_bwd_reduce_kernel<kGS, kEPI><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, dout, gm, mean, w, gamma, beta, mask, partial))));
+  if (dout2) { CL_GS(gm.GS, CL_EPI_BWD(epi, (cl_bwd_reduce_kernel<kGS, kEPI, true><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, dout, dout2, gm, mean, w, gamma, beta, mask, partial)))); }
+  else { CL_GS(gm.GS, CL_EPI_BWD(epi, (cl_bwd_reduce_kernel<kGS, kEPI, false><<<cl_grid(gm, nctas, gz), kT, 0, st>>>(x, dout, dout2, gm, mean, w, gamma, beta, mask, partial)))); }
 }
 void cl_bwd_finalize(const float* partial, int nrows, const Geom& gm, const BwdFin& fin, cudaStream_t st) {
   const dim3 b = fin_block(gm);
   CL_GS(gm.GS, (launch_k(cl_bwd_finalize_kernel<kGS>, dim3((gm.C / 4) / b.y), b, st, use_pdl(), partial, nrows, gm, fin)));
 }
-void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, int gz, int epi, const float* coef,
+void cl_bwd_apply(const float* x, const float* dout, const float* dout2, float* dx, const Geom& gm, int nctas, int gz, int epi, const float* coef,
                   const float* mean, const float* w, const float* gamma, const float* beta, const uint8_t* mask, float* dres,
                   cudaStream_t st) {
-  CL_GS(gm.GS, CL_EPI_BWD(epi, (launch_k(cl_bwd_apply_kernel<kGS, kEPI>, cl_grid(gm, nctas, gz), dim3(kT), st, use_pdl(), x, dout, dx, gm, coef, mean, w, gamma,
+  if (dout2) {
+    CL_GS(gm.GS, CL_EPI_BWD(epi, (launch_k(cl_bwd_apply_kernel<kGS, kEPI, true>, cl_grid(gm, nctas, gz), dim3(kT), st, use_pdl(), x, dout, dout2, dx, gm, coef, mean, w, gamma,
                                          beta, mask, dres))));
+  } else {
+    CL_GS(gm.GS, CL_EPI_BWD(epi, (launch_k(cl_bwd_apply_kernel<kGS, kEPI, false>, cl_grid(gm, nctas, gz), dim3(kT), st, use_pdl(), x, dout, dout2, dx, gm, coef, mean, w, gamma,
+                                         beta, mask, dres))));
+  }
 }
 
 }  // namespace dwt

@@ -71,10 +71,10 @@ void cl_stats(const float* x, const Geom& gm, int nctas, int gz, float* partial,
 void cl_fwd_finalize(const float* partial, int nrows, const float* shift, const Geom& gm, const FwdFin& fin, cudaStream_t st);
 void cl_apply(const float* x, float* y, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
               const float* gamma, const float* beta, const float* residual, uint8_t* mask, cudaStream_t st);
-void cl_bwd_reduce(const float* x, const float* dout, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
+void cl_bwd_reduce(const float* x, const float* dout, const float* dout2, const Geom& gm, int nctas, int gz, int epi, const float* mean, const float* w,
                    const float* gamma, const float* beta, const uint8_t* mask, float* partial, cudaStream_t st);
 void cl_bwd_finalize(const float* partial, int nrows, const Geom& gm, const BwdFin& fin, cudaStream_t st);
-void cl_bwd_apply(const float* x, const float* dout, float* dx, const Geom& gm, int nctas, int gz, int epi, const float* coef,
+void cl_bwd_apply(const float* x, const float* dout, const float* dout2, float* dx, const Geom& gm, int nctas, int gz, int epi, const float* coef,
                   const float* mean, const float* w, const float* gamma, const float* beta, const uint8_t* mask, float* dres,
                   cudaStream_t st);
 

@@ -127,10 +127,19 @@ class _NormFunction(torch.autograd.Function):
             x, save_mean, save_w, gamma_c, beta_c, mask = ctx.saved_tensors
         elif ctx.residual_mode == "aten":
             x, save_mean, save_w, gamma_c, beta_c, out = ctx.saved_tensors
+            extra = ctx.__dict__.pop("_dwt_extra_grad", None)
+            if extra is not None:
+                dout = dout + extra
             dout = torch.ops.aten.threshold_backward(dout, out, 0)
         else:
             x, save_mean, save_w, gamma_c, beta_c = ctx.saved_tensors
         kind, gs, n_domains, mode, eps, epi, n, c, hw, gshape = ctx.cfg
+        # second addend of the incoming gradient, left here by fork_for_sum's backward (see there): the channels-last
+        # kernels add it where they read dout; any other path adds it now
+        dout2 = ctx.__dict__.pop("_dwt_extra_grad", None)
+        if dout2 is not None and not ((mode & nv.LAYOUT_NHWC) and dout2.shape == dout.shape and dout2.dtype == torch.float32
+                                      and dout2.is_contiguous(memory_format=torch.channels_last)):
+            dout, dout2 = dout + dout2, None
         dout = dout.contiguous(memory_format=torch.channels_last) if (mode & nv.LAYOUT_NHWC) else dout.contiguous()
         dev = nv.require_cuda(dout)
         dx = torch.empty_like(x)
@@ -146,12 +155,12 @@ class _NormFunction(torch.autograd.Function):
         ws = nv.workspace(dev, n, c, hw, gs, n_domains)
         with torch.cuda.device(dev):
             if kind == "whiten":
-                rc = lib.dwt_whiten_bwd(nv.ptr(x), nv.ptr(dout), nv.ptr(dx), n, c, hw, gs, n_domains, mode, eps,
+                rc = lib.dwt_whiten_bwd(nv.ptr(x), nv.ptr(dout), nv.ptr(dout2), nv.ptr(dx), n, c, hw, gs, n_domains, mode, eps,
                                         nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(gamma_c), nv.ptr(beta_c), nv.ptr(mask),
                                         nv.ptr(d_res) if mask is not None else None, epi,
                                         nv.ptr(dgamma), nv.ptr(dbeta), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
             else:
-                rc = lib.dwt_bn_bwd(nv.ptr(x), nv.ptr(dout), nv.ptr(dx), n, c, hw, n_domains, mode,
+                rc = lib.dwt_bn_bwd(nv.ptr(x), nv.ptr(dout), nv.ptr(dout2), nv.ptr(dx), n, c, hw, n_domains, mode,
                                     nv.ptr(save_mean), nv.ptr(save_w), nv.ptr(gamma_c), nv.ptr(beta_c), nv.ptr(mask),
                                     nv.ptr(d_res) if mask is not None else None, epi,
                                     nv.ptr(dgamma), nv.ptr(dbeta), nv.ptr(ws), ws.numel(), nv.stream_ptr(dev))
@@ -159,6 +168,39 @@ class _NormFunction(torch.autograd.Function):
         if want_affine:
             dgamma, dbeta = dgamma.view(gshape), dbeta.view(gshape)
         return (dx, dgamma, dbeta, d_res) + (None,) * 9
+
+
+class _ForkForSum(torch.autograd.Function):
+    """a, b = fork(y): two aliases of y whose gradients are NOT summed by autograd.  y must be the output of a
+    _NormFunction node (the producer): backward hands the first gradient on as y's gradient and parks the second on the
+    producer's node, whose backward passes it to the kernels as the second addend (dwt_whiten_bwd's dout2).  If y gets
+    other gradients as well, autograd adds them to the first one as usual -- the parked addend is independent of that."""
+
+    @staticmethod
+    def forward(ctx, y):
+        ctx.producer = y.grad_fn
+        return y.view_as(y), y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        producer, ctx.producer = ctx.producer, None
+        if ga is None or gb is None:
+            return ga if gb is None else gb
+        if producer is None or "_dwt_extra_grad" in producer.__dict__:
+            return ga + gb
+        producer.__dict__["_dwt_extra_grad"] = gb
+        return ga
+
+
+def fork_for_sum(y):
+    """Use the output of a fused site twice -- e.g. as the next Bottleneck's input AND its identity branch
+    (resnet50_dwt_mec_officehome.py:217-240) -- without autograd's elementwise addition of the two gradients: returns
+    (a, b), two aliases of y.  Falls back to (y, y) when y was not produced by one of this package's norm sites or no
+    gradient is being recorded; results are identical either way."""
+    fn = getattr(y, "grad_fn", None)
+    if not torch.is_grad_enabled() or fn is None or not isinstance(fn, _NormFunction._backward_cls):
+        return y, y
+    return _ForkForSum.apply(y)
 
 
 def norm(x, gamma, beta, *, kind, group_size, n_domains, training_stats, eps, momentum, update_running,

@@ -134,11 +134,15 @@ class Bottleneck(_SiteOwner):
         if downsample is not None:
             self._add_site(layers, "downsample", f"layer{layer}.0.downsample_bn", planes * EXPANSION,
                            whiten, group_size, stats, site_mode)
+        # x feeds the first convolution AND the identity (or downsample) branch: with the fused sites the two gradients
+        # are summed inside the producing site's backward kernels instead of by an autograd `add` (layers.fork_for_sum)
+        object.__setattr__(self, "_fork", getattr(layers, "fork_for_sum", None) if site_mode == "fused" else None)
 
     def forward(self, x):
-        out = self._site("1", self.conv1(x), relu=True)
+        xa, xb = self._fork(x) if (self._fork is not None and self.training) else (x, x)
+        out = self._site("1", self.conv1(xa), relu=True)
         out = self._site("2", self.conv2(out), relu=True)
-        identity = x if self.downsample is None else self._site("downsample", self.downsample(x), relu=False)
+        identity = xb if self.downsample is None else self._site("downsample", self.downsample(xb), relu=False)
         return self._site("3", self.conv3(out), relu=True, residual=identity)
 
 

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define DWT_B200_ABI_VERSION 4
+#define DWT_B200_ABI_VERSION 5
 #define DWT_MAX_DOMAINS 4
 #define DWT_MAX_GROUP_SIZE 64
 
@@ -129,7 +129,7 @@ DWT_API int dwt_whiten_fwd(const float *x, float *y, int64_t N, int64_t C, int64
  * gradient of the identity branch -- is written there in the same pass (resnet50_dwt_mec_officehome.py:239-240).
  * Without RESIDUAL pass relu_mask = dresidual = NULL.
  */
-DWT_API int dwt_whiten_bwd(const float *x, const float *dout, float *dx, int64_t N, int64_t C, int64_t HW,
+DWT_API int dwt_whiten_bwd(const float *x, const float *dout, const float *dout2, float *dx, int64_t N, int64_t C, int64_t HW,
                    int group_size, int n_domains, int mode, float eps, const float *save_mean,
                    const float *save_w, const float *gamma, const float *beta, const uint8_t *relu_mask,
                    float *dresidual, int epilogue, float *dgamma, float *dbeta, void *workspace,
@@ -147,7 +147,7 @@ DWT_API int dwt_bn_fwd(const float *x, float *y, int64_t N, int64_t C, int64_t H
                uint8_t *relu_mask, int epilogue, float *save_mean, float *save_invstd, void *workspace,
                size_t workspace_bytes, dwt_stream_t stream);
 
-DWT_API int dwt_bn_bwd(const float *x, const float *dout, float *dx, int64_t N, int64_t C, int64_t HW,
+DWT_API int dwt_bn_bwd(const float *x, const float *dout, const float *dout2, float *dx, int64_t N, int64_t C, int64_t HW,
                int n_domains, int mode, const float *save_mean, const float *save_invstd,
                const float *weight, const float *bias, const uint8_t *relu_mask, float *dresidual, int epilogue,
                float *dweight, float *dbias, void *workspace, size_t workspace_bytes, dwt_stream_t stream);

@@ -375,6 +375,77 @@ def test_pointer_arguments_are_validated(dev):
     assert v0._version > ver                                                  # the in-place EMA is visible to autograd
 
 
+# --------------------------------------------------------------------------- fork_for_sum: gradient sum inside the kernels
+@pytest.mark.parametrize("fmt", ["nhwc", "nchw"])
+def test_fork_for_sum_equals_autograd_add(fmt, dev):
+    """A fused residual-tail site whose output feeds two consumers: with fork_for_sum the two gradients reach the
+    site's backward as dout and dout2 and are summed where they are read (channels-last kernels; the NCHW path adds them
+    with one ATen op inside backward).  fp32 addition of the same two numbers either way: bit-identical gradients."""
+    import dwt_b200
+    import whitening
+    torch.manual_seed(11)
+    c, gs, nper, hw = 64, 4, 4, 12
+    cl = fmt == "nhwc"
+
+    def tensor(*shape):
+        v = torch.randn(*shape, device=dev)
+        return v.contiguous(memory_format=torch.channels_last) if cl else v
+    x0, res0, w1, w2 = tensor(3 * nper, c, hw, hw), tensor(3 * nper, c, hw, hw), tensor(3 * nper, c, hw, hw), tensor(3 * nper, c, hw, hw)
+    g0, b0 = torch.rand(c, 1, 1, device=dev) + 0.5, 0.1 * torch.randn(c, 1, 1, device=dev)
+
+    def run(use_fork):
+        mods = [whitening.WTransform2d(c, gs).to(dev).train() for _ in range(3)]
+        site = dwt_b200.DomainTripleNorm("whiten", c, gs)
+        x, res = x0.clone().requires_grad_(True), res0.clone().requires_grad_(True)
+        gamma, beta = g0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        y = site(x, mods, gamma, beta, True, residual=res)
+        a, b = dwt_b200.fork_for_sum(y) if use_fork else (y, y)
+        if use_fork:
+            assert a is not y and a.data_ptr() == y.data_ptr()
+        ((a * w1).sum() + (b * b * w2).sum()).backward()
+        return x.grad, res.grad, gamma.grad, beta.grad
+    ref, got = run(False), run(True)
+    for name, r, g in zip(("dx", "dres", "dgamma", "dbeta"), ref, got):
+        assert torch.equal(r, g), (name, (r - g).abs().max().item())
+    # not the output of a site of this package: plain aliases, autograd adds as usual
+    t = torch.randn(4, device=dev, requires_grad=True) * 2
+    a, b = dwt_b200.fork_for_sum(t)
+    assert a is t and b is t
+    with torch.no_grad():
+        y = dwt_b200.DomainTripleNorm("whiten", c, gs)(x0, [whitening.WTransform2d(c, gs).to(dev).train() for _ in range(3)], g0, b0, True, residual=res0)
+        a, b = dwt_b200.fork_for_sum(y)
+        assert a is y and b is y
+
+
+def test_resnet_block_gradients_with_and_without_fork(dev):
+    """Whole harness model (fused sites, channels-last): every parameter gradient with the in-kernel gradient sum equals
+    the one with autograd's add."""
+    import dwt_b200
+    from harness.resnet50_dwt import Bottleneck, build_resnet50_dwt
+    from harness.synth import synth_batch, synth_state_dict
+    x, labels = synth_batch(seed=5, per_domain=2, size=64)
+    x = x.to(dev).contiguous(memory_format=torch.channels_last)
+
+    def grads(fork):
+        sd = {k: v.to(dev) for k, v in synth_state_dict(seed=1).items()}
+        model = build_resnet50_dwt(sd, dwt_b200, site_mode="fused", channels_last=True).to(dev).train()
+        if not fork:
+            for m in model.modules():
+                if isinstance(m, Bottleneck):
+                    object.__setattr__(m, "_fork", None)
+        model(x).square().mean().backward()
+        return {k: p.grad.clone() for k, p in model.named_parameters()}
+    det, bm = torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False     # same cuDNN algorithms in both runs
+    try:
+        a, b = grads(True), grads(False)
+    finally:
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = det, bm
+    worst = max(((a[k] - b[k]).abs().max().item() / (b[k].abs().max().item() + 1e-30), k) for k in a)
+    print("fork vs add: worst relative difference", worst)
+    assert worst[0] < 1e-6, worst          # measured: 0.0 (the same additions in another place)
+
+
 # --------------------------------------------------------------------------- channels-last max-pool (stem tail)
 @pytest.mark.parametrize("shape,k,s,p", [((6, 64, 112, 112), 3, 2, 1), ((3, 8, 9, 7), 3, 2, 1), ((2, 16, 8, 8), 2, 2, 0),
                                           ((2, 4, 5, 6), 3, 1, 1), ((1, 12, 7, 7), 5, 3, 2),
