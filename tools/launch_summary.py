@@ -6,7 +6,7 @@ import csv, re, sys, collections
 def family(name):
     n = name
     if "dwt::" in n:
-        m = re.search(r"(cl_[a-z_]+?|tc_[a-z_]+?|small_[a-z_]+?|tiled_[a-z_]+?|vec_reduce|head_loss|mec|fwd_factor|bwd_coef|partial_reduce|augment_pair|maxpool_[a-z]+)_kernel", n)
+        m = re.search(r"(cl_[a-z_]+?|tc_[a-z_]+?|small_[a-z_]+?|tiled_[a-z_]+?|vec_reduce|head_loss|mec|fwd_factor|bwd_coef|partial_reduce|augment_pair|maxpool_[a-z]+)(?:_3s2)?_kernel", n)
         return "dwt_b200: " + (m.group(1) if m else n[:40])
     low = n.lower()
     if "nchwtonhwc" in low or "nhwctonchw" in low: return "cuDNN layout conversion"
