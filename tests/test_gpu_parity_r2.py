@@ -449,7 +449,8 @@ def test_resnet_block_gradients_with_and_without_fork(dev):
 # --------------------------------------------------------------------------- channels-last max-pool (stem tail)
 @pytest.mark.parametrize("shape,k,s,p", [((6, 64, 112, 112), 3, 2, 1), ((3, 8, 9, 7), 3, 2, 1), ((2, 16, 8, 8), 2, 2, 0),
                                           ((2, 4, 5, 6), 3, 1, 1), ((1, 12, 7, 7), 5, 3, 2),
-                                          ((2, 8, 10, 6), 3, 2, 1), ((3, 4, 2, 2), 3, 2, 1), ((2, 12, 8, 8), 3, 2, 1)])
+                                          ((2, 8, 10, 6), 3, 2, 1), ((3, 4, 2, 2), 3, 2, 1), ((2, 12, 8, 8), 3, 2, 1),
+                                          ((2, 8, 8, 12), 3, 2, 1), ((1, 4, 4, 4), 3, 2, 1)])
 def test_maxpool_is_bit_exact_vs_torch(shape, k, s, p, dev):
     """dwt_b200.MaxPool2d == F.max_pool2d forward AND backward, bit for bit: post-ReLU inputs are full of ties (windows
     of zeros), and the gradient must go to the same element (first maximum in row-major window order)."""

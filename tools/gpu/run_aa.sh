@@ -1,7 +1,7 @@
 #!/bin/bash
-# round-2 GPU call AA (1 GPU): 2x2-patch max-pool backward for the stem geometry
+# round-2 GPU call AA (1 GPU): 2x2-patch max-pool kernels for the stem geometry (backward, then forward)
 mkdir -p gpurun_out/aa
-timeout 600 python -m pytest tests/test_gpu_parity_r2.py tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "maxpool or resnet_224 or resnet_tiny" > gpurun_out/aa/pytest_pool.log 2>&1; echo "pytest pool rc=$?"
+timeout 600 python -m pytest tests/test_gpu_parity_r2.py tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "maxpool or resnet_224 or resnet_tiny or fork" > gpurun_out/aa/pytest_pool.log 2>&1; echo "pytest pool rc=$?"
 grep -E "passed|failed|error" gpurun_out/aa/pytest_pool.log | tail -3
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/aa/smoke.log 2>&1; echo "smoke rc=$?"
 timeout 600 python bench.py --steps 20 --warmup 5 --no-extras --no-cpu-baseline > gpurun_out/aa/bench.json 2> gpurun_out/aa/bench.err; echo "bench rc=$?"
