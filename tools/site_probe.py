@@ -14,6 +14,7 @@ def main():
     dev = torch.device("cuda", 0)
     which = [int(a) for a in sys.argv[1:] if a.isdigit()] or range(len(SITES))
     cl = "cl" in sys.argv
+    tail = "tail" in sys.argv           # residual tail + two gradient addends (fork_for_sum): the Bottleneck's last site
     iters = 3
     res = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -25,6 +26,15 @@ def main():
             x = x.contiguous(memory_format=torch.channels_last)
         x.requires_grad_(True)
         dout = torch.randn_like(x)
+        res_in = torch.randn_like(x).requires_grad_(True) if tail else None
+        dout2 = torch.randn_like(x) if tail else None
+
+        def fwd_bwd():
+            if not tail:
+                site(x, mods, g, b, relu=True).backward(dout)
+                return
+            a, bb = dwt_b200.fork_for_sum(site(x, mods, g, b, True, residual=res_in))
+            torch.autograd.backward([a, bb], [dout, dout2])
         if kind == "whiten":
             mods = [dwt_b200.WTransform2d(c, gs).to(dev).train() for _ in range(3)]
         else:
@@ -33,14 +43,12 @@ def main():
         site = dwt_b200.DomainTripleNorm(kind, c, gs)
         g = torch.ones(c, 1, 1, device=dev, requires_grad=True); b = torch.zeros(c, 1, 1, device=dev, requires_grad=True)
         for _ in range(2):
-            out = site(x, mods, g, b, relu=True); out.backward(dout)
+            fwd_bwd()
         torch.cuda.synchronize()
         _native.profile_begin()
         for _ in range(iters):
             flush.zero_()                      # cold L2 between iterations
-            out = site(x, mods, g, b, relu=True)
-            flush.zero_()
-            out.backward(dout)
+            fwd_bwd()
         prof = _native.profile_end()
         for k, v in prof.items():
             res[k] = dict(us=1e3 * v["ms"] / v["launches"], gbs=v["bytes"] / v["ms"] / 1e6)
