@@ -158,3 +158,18 @@ def test_replicated_site_bookkeeping_errors_and_counters(built_lib):
         dwt_b200.DomainTripleNorm("bn", 8)(torch.randn(2, 8, 4, 4), bns, torch.ones(8, 1, 1), torch.zeros(8, 1, 1),
                                            replicated=True)
     assert [int(m.num_batches_tracked) for m in bns] == [1, 1, 1]
+
+
+def test_fork_for_sum_is_the_identity_without_a_site_output():
+    """fork_for_sum only changes how gradients are summed when its argument is the output of one of the package's norm
+    sites; anything else (and anything under no_grad) comes back as the same object twice, so autograd adds as usual."""
+    import torch
+    import dwt_b200
+    t = (torch.randn(3, 4, requires_grad=True) * 2.0)
+    a, b = dwt_b200.fork_for_sum(t)
+    assert a is t and b is t
+    (a.sum() + (b * b).sum()).backward()
+    with torch.no_grad():
+        u = torch.randn(2, 2)
+        a, b = dwt_b200.fork_for_sum(u)
+        assert a is u and b is u
