@@ -4,7 +4,9 @@ tile -- producer: TMA issued; transform warp (quarter 0 of the tile's set): tile
 MMA issuer: `ready` seen, MMAs + commits issued."""
 import os, sys
 HERE = os.path.dirname(os.path.abspath(__file__))
-os.environ["DWT_B200_LIB"] = os.path.join(HERE, "libdwt_b200_gramprof.so")
+sys.path.insert(0, HERE)
+import _variant
+os.environ["DWT_B200_LIB"] = _variant.build("gramprof", "DWT_PROF_GRAM", "norm_tc.cu")
 sys.path.insert(0, os.path.join(HERE, "..", "..", "..", "dwt-domain-adaptation_b200"))
 import torch
 import dwt_b200
