@@ -109,3 +109,39 @@ def test_module_surface_is_the_references_own():
             if kw.get("track_running_stats", True):
                 v1 = {k: v for k, v in a.state_dict().items() if "num_batches" not in k}
                 a.load_state_dict(v1)                             # pre-version-2 checkpoint: no counter
+
+
+def test_space_to_depth_stem_equals_the_reference_stem(monkeypatch):
+    """The harness option stem_s2d (7x7/2 convolution evaluated as the 4x4/1 convolution of the 2x2 space-to-depth image)
+    against the UNMODIFIED reference model's conv1: same output and the same gradient of the [64, 3, 7, 7] weight (fp32
+    summation order is the only difference), in both memory formats; and the whole model's logits on top of it.  (The
+    GPU golden test at 224x224 runs the same option on the CUDA layers.)"""
+    import importlib
+    import oracle.torch_port as port
+    from harness.resnet50_dwt import build_resnet50_dwt
+    from harness.synth import synth_batch, synth_state_dict
+    monkeypatch.syspath_prepend(os.path.join(REF, "utils"))
+    monkeypatch.syspath_prepend(REF)
+    monkeypatch.chdir(REF)
+    ref_script = importlib.import_module("resnet50_dwt_mec_officehome")
+    torch.set_num_threads(8)
+    sd = synth_state_dict(1)
+    x, _ = synth_batch(3, 2, size=64)
+    clone = lambda: {k: v.clone() for k, v in sd.items()}
+    ref = ref_script.ResNet(ref_script.Bottleneck, [3, 4, 6, 3], clone())
+    ref.load_state_dict(clone(), strict=False)
+    ref.train()
+    probe = torch.randn(6, 64, 32, 32)
+    r_stem = ref.conv1(x)
+    (gr,) = torch.autograd.grad((r_stem * probe).sum(), ref.conv1.weight)
+    r_logits = ref(x)
+    for cl in (False, True):
+        mine = build_resnet50_dwt(clone(), port, channels_last=cl, stem_s2d=True).train()
+        xi = x.contiguous(memory_format=torch.channels_last) if cl else x
+        assert mine.conv1.weight.shape == ref.conv1.weight.shape == (64, 3, 7, 7)
+        m_stem = mine._stem(xi)
+        assert m_stem.shape == r_stem.shape and torch.allclose(r_stem, m_stem, atol=1e-5), (r_stem - m_stem).abs().max()
+        (gm,) = torch.autograd.grad((m_stem * probe).sum(), mine.conv1.weight)
+        assert (gr - gm).norm() <= 1e-5 * gr.norm(), ((gr - gm).norm() / gr.norm()).item()
+        # 2 x 2 pixels per image reach layer4 at this size: the batch statistics amplify the rounding differences
+        assert (r_logits - mine(xi)).abs().max() <= 1e-3 * r_logits.abs().max()
