@@ -10,11 +10,11 @@
 //
 //   warp 0      TMA producer: cp.async.bulk.tensor.3d (box 32 px x 64 ch x 1 image, SWIZZLE_128B)
 //               into a shared-memory ring, mbarrier complete_tx.
-//   warps 2-9   transform the landed tile for the tensor core (below), row sums in registers.
-//   warp 1      MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::tf32, fp32 accumulator in
-//               TMEM; tcgen05.commit releases the stage back to the producer.  Operands are K-major straight
-//               from the swizzled tile (NCHW rows ARE K-major: the reference's transposing copy,
-//               whitening.py:46, disappears).
+//   warps 2-9   transform the landed tile for the tensor core (below).
+//   warp 1      MMA issuer (the Gram kernel has a second one, warp 10): one elected lane, warp-uniform operands,
+//               tcgen05.mma.cta_group::1.kind::tf32, fp32 accumulator in TMEM; tcgen05.commit releases the stage back
+//               to the producer.  Operands are K-major straight from the swizzled tile (NCHW rows ARE K-major: the
+//               reference's transposing copy, whitening.py:46, disappears).
 //   epilogue    tcgen05.ld the accumulator -> per-CTA partial -> global.  The fixed-order reduction of the
 //               partials and the dense algebra (Cholesky / inverse / EMA, or the backward coefficients) run
 //               as the small follow-up launches of norm_dense.cu.
@@ -22,17 +22,16 @@
 // stats (tc_gram_kernel) -- SPLIT precision.  The covariance feeds a Cholesky factor whose error is the Gram
 // error times the condition number (the eps = 1e-3 shrinkage is absolute and stops helping once activations are
 // large), so a single tf32 pass is not enough (y errors of 1e-3..5e-3 at cond >= 1e4).  Each centred
-// sample s = x - K is split hi = trunc_tf32(s) (what the tensor core reads of an fp32 word anyway) and
-// lo = RN_tf32(s - hi), and
-//       G = HH + LH + LH^T         HH = sum hi hi^T,  LH = sum lo hi^T        (lo lo^T ~ 2^-20 G is dropped)
-// comes out of ONE M=128 N=80 K=8 MMA per 8 pixels: the A operand [hi ; lo] (128 rows: TMEM lanes 0..63 = hi of channels
-// 0..63, lanes 64..127 = their lo) is written to TENSOR MEMORY by the transform warps (tcgen05.st, lane = row; a warp
-// may only touch its own 32-lane quarter, so warps are hi warps or lo warps), the B operand is the hi tile written
-// back in place plus 16 constant rows (a row of ones: accumulator column 64 = the row sums the mean needs).  Tiles
-// alternate between two accumulators so that two dependent tcgen05.mma chains are in flight per CTA.
-// hi = RN_tf32(s), lo = s - hi.  Measured on B200 (tests/test_gpu_parity_r2.py): covariance error 6e-8 (single tf32
-// pass: 4e-6), y error at cond 1e3 / 1e4 3.6e-6 / 2.3e-5 (single pass 1.2e-4 / 2.9e-4, the fp32 reference itself
-// 3.2e-5 / 2.1e-4).
+// sample s = x - K is split hi = trunc_tf32(s) (what the tensor core reads of an fp32 word anyway: no instruction) and
+// lo = s - hi (exact in fp32; the core keeps its top 11 bits), and
+//       G = HH + LH + LH^T         HH = sum hi hi^T,  LH = sum lo hi^T        (lo lo^T ~ 3e-7 G is dropped)
+// comes out of ONE M=128 N=80 K=8 MMA per 8 pixels: the A operand (128 rows = TMEM lanes; quarter q carries channels
+// 16q..16q+15, s in lanes 0..15 and lo in lanes 16..31) is written to TENSOR MEMORY by the transform warps (tcgen05.st; a
+// warp may only touch its own 32-lane quarter), the B operand is the tile of s written back in place plus 16 constant rows
+// (a row of ones: accumulator column 64 = the row sums the mean needs).  Tiles alternate between two transform sets, two
+// MMA-issuing warps and two accumulators.  Measured on B200 (tests/test_gpu_parity_r2.py): running-covariance error 8e-8
+// (single tf32 pass: 4e-6), y error at cond 1e3 / 1e4 3.6e-6 / 2.3e-5 (single pass 1.2e-4 / 2.9e-4, the fp32 reference
+// itself 3.1e-5 / 2.0e-4).  What bounds it (0.73 of the HBM peak): profiles/ncu_r02_tc_gram.md.
 //
 // bwd_reduce (tc_contract_kernel) -- single pass: R multiplies already-formed W's in the coefficient algebra and
 // its tf32 product errors are zero-mean over M >= 4096 samples (round-to-nearest operands).
