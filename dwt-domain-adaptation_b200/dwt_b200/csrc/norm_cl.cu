@@ -30,6 +30,9 @@
 // The residual tail relu(z + identity) (resnet50_dwt_mec_officehome.py:239-240): the forward apply leaves one
 // byte per float4 with the four (out > 0) bits; the backward passes mask dout with it (the pre-activation cannot
 // be recomputed without the residual) and bwd_apply also writes the masked gradient for the identity branch.
+// Such a site's output is used twice by the next block (first convolution and identity branch): the two gradients
+// arrive as dout and dout2 and are summed where they are read (template flag D2; dwt_b200.h, functional.fork_for_sum)
+// instead of by an elementwise kernel in between.
 //
 // Reference semantics: utils/whitening.py:37-61, utils/batch_norm.py:54-69 (/root/reference).
 #include <stdlib.h>
