@@ -378,6 +378,8 @@ def workload_config(args, per_domain):
 def implementation_note(args):
     seg = getattr(args, "grad_segments", 1)
     return {"site_mode": args.site_mode, "memory_format": args.memory_format,
+            "block_input_gradients": ("summed inside the producing site's backward kernels (dwt_b200.fork_for_sum)"
+                                      if getattr(args, "grad_fork", True) else "summed by autograd (aten::add)"),
             "stem": ("7x7/2 stem convolution evaluated as the 4x4/1 convolution of the 2x2 space-to-depth image (same arithmetic, "
                      "cuDNN tensor-core kernel)" if getattr(args, "stem", DEFAULT_STEM) == "s2d" else "7x7/2 convolution on the 3-channel image"),
             "launch": "CUDA-graph replay of the whole step" if args.cuda_graph else "eager",
